@@ -1,0 +1,169 @@
+"""ctypes binding of libsd_b200.so (the C-ABI declared in include/sd_b200.h) and its in-tree build.
+
+PyTorch is plumbing here: it owns device memory and streams; every compute call goes through one C-ABI
+symbol with raw ``tensor.data_ptr()`` pointers and the current CUDA stream.  There is no CPU fallback: if the
+shared library is missing, or the process has no sm_100 device, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import sys
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libsd_b200.so")
+SOURCES = ["lif.cu", "vq.cu", "conv_simt.cu", "conv_tc.cu", "sample.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--extended-lambda",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--shared", "-cudart", "shared"]
+
+# Exported symbols of include/sd_b200.h (tests check that the library exports exactly these).
+SYMBOLS = [
+    "sd_last_error", "sd_version", "sd_device_info", "sd_stf_guard", "sd_stf_rows", "sd_stf_bytes",
+    "sd_stf_from_nchw", "sd_stf_to_nchw", "sd_channel_affine", "sd_state_convert", "sd_lif_forward", "sd_memout", "sd_vq_feature", "sd_vq_lookup",
+    "sd_vq_gather", "sd_conv_weight_bytes_simt", "sd_conv_weight_bytes_tc", "sd_conv_pack_weights_simt",
+    "sd_conv_pack_weights_tc", "sd_conv_lif_simt", "sd_conv_lif_tc", "sd_conv_tc_supported", "sd_philox_uniform",
+    "sd_philox_exponential", "sd_philox_offset_increment", "sd_sample_step", "sd_denoiser_input", "sd_to_uint8",
+]
+
+
+class SdError(RuntimeError):
+    """A non-zero return code from libsd_b200 (SD_ERR_CUDA / SD_ERR_NO_DEVICE / SD_ERR_UNSUPPORTED)."""
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "sd_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into spiking-diffusion_b200/libsd_b200.so (in-tree, travels with gpurun)."""
+    if not force and not _stale():
+        return LIB_PATH
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f not in ("--shared",)] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [c for c in cmd if c not in ("-cudart", "shared")]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+        if verbose and out.strip():
+            print(out)
+    cmd = [_nvcc(), "--shared", "-cudart", "shared", "-o", LIB_PATH] + objs
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout)
+    return LIB_PATH
+
+
+class ConvDesc(ctypes.Structure):
+    """struct sd_conv_desc (include/sd_b200.h)."""
+    _fields_ = [(n, ctypes.c_int) for n in
+                ("T", "B", "C_in", "H_in", "W_in", "C_out", "H_out", "W_out", "kh", "kw", "stride", "pad",
+                 "transposed", "in_kind", "out_kind", "in_T", "C_in0")] + \
+               [("tau", ctypes.c_float), ("v_threshold", ctypes.c_float), ("v_reset", ctypes.c_float),
+                ("hard_reset", ctypes.c_int), ("nsplit", ctypes.c_int)]
+
+
+class ConvArgs(ctypes.Structure):
+    """struct sd_conv_args (include/sd_b200.h)."""
+    _fields_ = [("in_", ctypes.c_void_p), ("in2", ctypes.c_void_p), ("weights", ctypes.c_void_p),
+                ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p), ("v", ctypes.c_void_p),
+                ("out", ctypes.c_void_p), ("out_sum", ctypes.c_void_p), ("memout_coef_host", ctypes.c_void_p)]
+
+
+IN_REAL_CONST, IN_REAL_SEQ, IN_STF = 0, 1, 2
+OUT_LIF, OUT_REAL_SEQ, OUT_MEMOUT_TANH, OUT_MEAN_T = 0, 1, 2, 3
+SD_ERR_INVALID, SD_ERR_CUDA, SD_ERR_NO_DEVICE, SD_ERR_UNSUPPORTED = 1, 2, 3, 4
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def _declare(lib: ctypes.CDLL) -> None:
+    i, i64, u64, f, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_float, ctypes.c_void_p
+    pd, pa = ctypes.POINTER(ConvDesc), ctypes.POINTER(ConvArgs)
+    sig = {
+        "sd_last_error": (ctypes.c_char_p, []),
+        "sd_version": (i, []),
+        "sd_device_info": (i, [ctypes.POINTER(i)] * 4),
+        "sd_stf_guard": (i64, [i]),
+        "sd_stf_rows": (i64, [i, i, i]),
+        "sd_stf_bytes": (i64, [i, i, i, i, i]),
+        "sd_stf_from_nchw": (i, [vp, vp, i, i, i, i, i, vp]),
+        "sd_stf_to_nchw": (i, [vp, vp, i, i, i, i, i, vp]),
+        "sd_channel_affine": (i, [vp, vp, vp, vp, i64, i, i64, vp]),
+        "sd_state_convert": (i, [vp, vp, i, i, i, i, i, vp]),
+        "sd_lif_forward": (i, [vp, vp, vp, vp, i, i64, f, f, f, i, i, vp]),
+        "sd_memout": (i, [vp, vp, vp, i, i64, i, vp]),
+        "sd_vq_feature": (i, [vp, vp, vp, vp, i, i, i, i, i, vp]),
+        "sd_vq_lookup": (i, [vp, vp, vp, vp, i64, i, i, vp]),
+        "sd_vq_gather": (i, [vp, vp, vp, i, i, i, i, i, vp]),
+        "sd_conv_weight_bytes_simt": (i64, [pd]),
+        "sd_conv_weight_bytes_tc": (i64, [pd]),
+        "sd_conv_pack_weights_simt": (i, [pd, vp, vp, vp]),
+        "sd_conv_pack_weights_tc": (i, [pd, vp, vp, vp, vp]),
+        "sd_conv_lif_simt": (i, [pd, pa, vp]),
+        "sd_conv_lif_tc": (i, [pd, pa, vp]),
+        "sd_conv_tc_supported": (i, [pd]),
+        "sd_philox_uniform": (i, [vp, i64, u64, u64, i64, i64, ctypes.POINTER(u64), vp]),
+        "sd_philox_exponential": (i, [vp, i64, u64, u64, i64, i64, ctypes.POINTER(u64), vp]),
+        "sd_philox_offset_increment": (i, [i64, ctypes.POINTER(u64)]),
+        "sd_sample_step": (i, [vp, vp, vp, vp, i64, i, i, f, u64, u64, u64, i64, i64, vp]),
+        "sd_denoiser_input": (i, [vp, vp, i, i, i, i, vp]),
+        "sd_to_uint8": (i, [vp, vp, i64, vp]),
+    }
+    assert set(sig) == set(SYMBOLS)
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded C-ABI library.  Raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SdError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU or PyTorch fallback for the CUDA path)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def check(rc: int) -> None:
+    """Map a C-ABI return code onto the exception type the reference raises on the same condition:
+    SD_ERR_INVALID -> ValueError (SJ/activation_based/layer.py:169-170, neuron.py:92-94,707), others -> SdError."""
+    if rc == 0:
+        return
+    msg = lib().sd_last_error().decode("utf-8", "replace")
+    if rc == SD_ERR_INVALID:
+        raise ValueError(msg)
+    raise SdError(f"libsd_b200 error {rc}: {msg}")
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t) -> Optional[int]:
+    return None if t is None else t.data_ptr()

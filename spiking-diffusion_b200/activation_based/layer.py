@@ -1,0 +1,186 @@
+"""Step-mode layer wrappers and the fused container.
+
+``Conv2d`` / ``ConvTranspose2d`` / ``BatchNorm2d`` keep the constructor signatures, parameter names and the
+``step_mode`` protocol of SJ/activation_based/layer.py:125-173, 276-325, 423-465, so reference ``state_dict``s load
+unchanged.  Called on their own they run a single un-fused sm_100a kernel each.  ``SpikingSequential`` is the
+``nn.Sequential`` the models are built from: it recognises conv -> BN -> LIF triplets (and a bare trailing conv)
+and runs each as ONE fused kernel, with spike tensors staying in the packed STF layout between stages.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import _lib, engine
+from .._lib import check, lib, ptr, stream_ptr
+from . import base, neuron
+
+
+def _check_5d(x: torch.Tensor):
+    # same condition, message shape and exception type as SJ/activation_based/layer.py:169-170
+    if x.dim() != 5:
+        raise ValueError(f"expected x with shape [T, N, C, H, W], but got x with shape {x.shape}!")
+
+
+class _ConvMixin(base.StepModule):
+    def _plan(self, T, B, H, W) -> engine.FusedLayer:
+        key = (T, B, H, W, self.weight.data_ptr(), self.weight._version,
+               None if self.bias is None else self.bias._version)
+        if getattr(self, "_plan_key", None) != key:
+            self._plan_obj = engine.FusedLayer(self, None, None, T=T, B=B, H_in=H, W_in=W,
+                                               in_kind=_lib.IN_REAL_SEQ, out_kind=_lib.OUT_REAL_SEQ, impl="simt")
+            self._plan_key = key
+        return self._plan_obj
+
+    def _forward_any(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("layer forward needs CUDA tensors: spiking_diffusion_b200 has no CPU path")
+        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad) and self.training:
+            raise NotImplementedError("training (autograd) is not implemented in this round (SURVEY.md 8(f) rank 1)")
+        if self.step_mode == "s":
+            if x.dim() != 4:
+                raise ValueError(f"expected x with shape [N, C, H, W], but got x with shape {x.shape}!")
+            x5 = x.unsqueeze(0)
+        else:
+            _check_5d(x)
+            x5 = x
+        T, B, _, H, W = x5.shape
+        plan = self._plan(T, B, H, W)
+        out = plan.alloc_out()
+        plan.run(x5.contiguous().float(), out)
+        return out[0] if self.step_mode == "s" else out
+
+
+class Conv2d(nn.Conv2d, _ConvMixin):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 padding_mode="zeros", step_mode="s"):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, padding_mode)
+        self.step_mode = step_mode
+
+    def extra_repr(self):
+        return super().extra_repr() + f", step_mode={self.step_mode}"
+
+    def forward(self, x: torch.Tensor):
+        return self._forward_any(x)
+
+
+class ConvTranspose2d(nn.ConvTranspose2d, _ConvMixin):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, output_padding=0, groups=1,
+                 bias=True, dilation=1, padding_mode="zeros", step_mode="s"):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, output_padding, groups, bias,
+                         dilation, padding_mode)
+        self.step_mode = step_mode
+
+    def extra_repr(self):
+        return super().extra_repr() + f", step_mode={self.step_mode}"
+
+    def forward(self, x: torch.Tensor):
+        return self._forward_any(x)
+
+
+class BatchNorm2d(nn.BatchNorm2d, base.StepModule):
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True, step_mode="s"):
+        super().__init__(num_features, eps, momentum, affine, track_running_stats)
+        self.step_mode = step_mode
+
+    def extra_repr(self):
+        return super().extra_repr() + f", step_mode={self.step_mode}"
+
+    def forward(self, x: torch.Tensor):
+        if not x.is_cuda:
+            raise RuntimeError("layer forward needs CUDA tensors: spiking_diffusion_b200 has no CPU path")
+        if self.training or not self.track_running_stats:
+            raise NotImplementedError("train-mode BatchNorm (batch statistics) is not implemented in this round")
+        if self.step_mode == "m":
+            _check_5d(x)
+        elif x.dim() != 4:
+            raise ValueError(f"expected x with shape [N, C, H, W], but got x with shape {x.shape}!")
+        scale, shift = engine.fold_bn(None, self.num_features, self, x.device)
+        xc = x.contiguous().float()
+        out = torch.empty_like(xc)
+        C = xc.shape[-3]
+        hw = xc.shape[-1] * xc.shape[-2]
+        check(lib().sd_channel_affine(ptr(xc), ptr(scale), ptr(shift), ptr(out), xc.numel() // (C * hw), C, hw,
+                                      stream_ptr()))
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+class SpikingSequential(nn.Sequential):
+    """``nn.Sequential`` of (conv, BN, LIF) triplets executed as fused kernels.
+
+    Same child names as a plain ``nn.Sequential`` -> same ``state_dict`` keys as the reference
+    (e.g. ``encoder.snn_convs.{0,1,3,4,6,7}.*``).  Input and output use the reference's tensor format, fp32
+    ``[T, N, C, H, W]``; in between, spikes stay in the STF layout.  LIF state follows the reference's
+    protocol: each ``LIFNode.v`` persists between calls until ``reset()``.
+    """
+
+    def _stages(self) -> List[Tuple[nn.Module, Optional[nn.Module], Optional[nn.Module]]]:
+        mods = list(self.children())
+        out, i = [], 0
+        while i < len(mods):
+            conv = mods[i]
+            if not isinstance(conv, (nn.Conv2d, nn.ConvTranspose2d)):
+                raise TypeError(f"SpikingSequential expects conv[-BN][-LIF] groups, got {type(conv).__name__} at {i}")
+            bn = mods[i + 1] if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm2d) else None
+            j = i + 1 + (bn is not None)
+            lif = mods[j] if j < len(mods) and isinstance(mods[j], neuron.LIFNode) else None
+            i = j + (lif is not None)
+            out.append((conv, bn, lif))
+        return out
+
+    def _build(self, T, B, H, W, device):
+        stages = self._stages()
+        plans, h, w = [], H, W
+        for k, (conv, bn, lif) in enumerate(stages):
+            in_kind = _lib.IN_REAL_SEQ if k == 0 else _lib.IN_STF
+            if lif is not None:
+                out_kind = _lib.OUT_LIF
+            else:
+                if k != len(stages) - 1:
+                    raise TypeError("a conv without LIF is only supported as the last stage")
+                out_kind = _lib.OUT_REAL_SEQ
+            if bn is not None and (bn.training or not bn.track_running_stats):
+                raise NotImplementedError("train-mode BatchNorm (batch statistics) is not implemented in this round")
+            fl = engine.FusedLayer(conv, bn, lif, T=T, B=B, H_in=h, W_in=w, in_kind=in_kind, out_kind=out_kind,
+                                   impl="simt" if k == 0 else "auto")
+            plans.append(fl)
+            h, w = fl.H_out, fl.W_out
+        return stages, plans
+
+    def forward(self, x: torch.Tensor):
+        if not x.is_cuda:
+            raise RuntimeError("SpikingSequential.forward needs CUDA tensors: spiking_diffusion_b200 has no CPU path")
+        _check_5d(x)
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("training (autograd) is not implemented in this round (SURVEY.md 8(f) rank 1)")
+        T, B, _, H, W = x.shape
+        key = (T, B, H, W, x.device, tuple(p._version for p in self.parameters()),
+               tuple(b._version for b in self.buffers()))
+        if getattr(self, "_key", None) != key:
+            self._stage_list, self._plans = self._build(T, B, H, W, x.device)
+            self._bufs = [p.alloc_out() for p in self._plans]
+            self._key = key
+        cur = x.contiguous().float()
+        for (conv, bn, lif), plan, buf in zip(self._stage_list, self._plans, self._bufs):
+            v_planar = None
+            if lif is not None:
+                d = plan.desc
+                v_planar = plan.alloc_state()
+                if isinstance(lif.v, torch.Tensor):  # continue from the stored state (neuron.py:972-1010)
+                    check(lib().sd_state_convert(ptr(lif.v.contiguous().float()), ptr(v_planar), d.B, d.C_out, d.H_out,
+                                                 d.W_out, 1, stream_ptr()))
+            out = buf if plan.desc.out_kind == _lib.OUT_LIF else plan.alloc_out()
+            plan.run(cur, out, v=v_planar)
+            if lif is not None:
+                d = plan.desc
+                v_new = torch.empty((d.B, d.C_out, d.H_out, d.W_out), dtype=torch.float32, device=x.device)
+                check(lib().sd_state_convert(ptr(v_planar), ptr(v_new), d.B, d.C_out, d.H_out, d.W_out, 0, stream_ptr()))
+                lif.v = v_new
+            cur = out
+        last = self._plans[-1].desc
+        if last.out_kind == _lib.OUT_LIF:
+            return engine.stf_to_nchw(cur, last.T, last.B, last.C_out, last.H_out, last.W_out)
+        return cur

@@ -1,0 +1,263 @@
+// CUDA-core fused conv -> BN -> LIF (and the three non-spiking tails), fp32 accumulation.
+//
+// This is the path for the layers that are NOT tensor-core shaped:
+//   * real-valued inputs with a tiny contraction (enc.conv1 K=9, den.conv1 K=18, vq.poisson K=16) whose input
+//     is identical at every timestep (R/main.py:133, R/snn_model/vq_diffusion.py:198, vae_model.py:56), so
+//     the convolution is evaluated ONCE and the LIF runs on a constant current;
+//   * the stride-2 / transposed layers of the VQ-VAE (0.06 % of the sampling FLOPs).
+// It is also the exact-order fp32 cross-check for the tcgen05 kernel in tests.
+//
+// Mapping: one thread = one output neuron (b, oy, ox, co) for ALL T timesteps; co is the fastest index in a
+// warp so packed weights [tap][ci][co] are read coalesced and the input element is a warp-wide broadcast.
+// Spike inputs are read 8 channels (16 B) at a time from the STF planes.
+#include "common.cuh"
+
+namespace sd {
+
+struct SimtParams {
+  sd_conv_desc d;
+  const void* in;
+  const void* in2;
+  const float* w;       // [kh*kw][C_in][C_out]
+  const float* scale;
+  const float* shift;
+  float* v;
+  void* out;
+  __half* out_sum;
+  MemoutCoef coef;
+  float decay_keep;
+};
+
+template <int TMAX>
+__global__ void __launch_bounds__(256) conv_simt_kernel(const SimtParams p) {
+  const sd_conv_desc& d = p.d;
+  const int T = d.T;
+  const int Cout = d.C_out, Cin = d.C_in;
+  const int64_t total = (int64_t)d.B * d.H_out * d.W_out * Cout;
+  const StfGeom gin(d.B, d.H_in, d.W_in);
+  const StfGeom gout(d.B, d.H_out, d.W_out);
+  const int Cin8_0 = c8(d.C_in0), Cin8_1 = c8(Cin - d.C_in0);
+  const int Cout8 = c8(Cout);
+  const bool const_in = d.in_kind == SD_IN_REAL_CONST;
+  const int TA = const_in ? 1 : (d.in_kind == SD_IN_STF ? d.in_T : T);  // timesteps actually convolved
+
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    int64_t r = i / Cout;
+    const int ox = (int)(r % d.W_out); r /= d.W_out;
+    const int oy = (int)(r % d.H_out);
+    const int b = (int)(r / d.H_out);
+
+    float acc[TMAX];
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) acc[t] = 0.f;
+
+    for (int ky = 0; ky < d.kh; ++ky) {
+      int iy;
+      if (d.transposed) {
+        int ny = oy + d.pad - ky;
+        if (ny < 0 || ny % d.stride) continue;
+        iy = ny / d.stride;
+      } else {
+        iy = oy * d.stride - d.pad + ky;
+      }
+      if (iy < 0 || iy >= d.H_in) continue;
+      for (int kx = 0; kx < d.kw; ++kx) {
+        int ix;
+        if (d.transposed) {
+          int nx = ox + d.pad - kx;
+          if (nx < 0 || nx % d.stride) continue;
+          ix = nx / d.stride;
+        } else {
+          ix = ox * d.stride - d.pad + kx;
+        }
+        if (ix < 0 || ix >= d.W_in) continue;
+        const float* wt = p.w + (int64_t)(ky * d.kw + kx) * Cin * Cout + co;
+        if (d.in_kind == SD_IN_STF) {
+          const int64_t row = gin.row(b, iy, ix);
+          for (int cc = 0; cc < Cin; cc += 8) {
+            const bool seg1 = cc >= d.C_in0;
+            const __half* base = seg1 ? (const __half*)p.in2 : (const __half*)p.in;
+            const int C8s = seg1 ? Cin8_1 : Cin8_0;
+            const int cl = seg1 ? cc - d.C_in0 : cc;
+            float wv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) wv[j] = (cc + j < Cin) ? wt[(int64_t)(cc + j) * Cout] : 0.f;
+#pragma unroll
+            for (int t = 0; t < TMAX; ++t) {
+              if (t < TA) {
+                const uint4 raw = *reinterpret_cast<const uint4*>(base + gin.at(t, C8s, cl, row));
+                const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float2 f = __half22float2(h2[j]);
+                  acc[t] = fmaf(f.x, wv[2 * j], acc[t]);
+                  acc[t] = fmaf(f.y, wv[2 * j + 1], acc[t]);
+                }
+              }
+            }
+          }
+        } else {
+          const float* xin = (const float*)p.in;
+          const int64_t plane = (int64_t)d.H_in * d.W_in;
+          for (int ci = 0; ci < Cin; ++ci) {
+            const float wv = wt[(int64_t)ci * Cout];
+#pragma unroll
+            for (int t = 0; t < TMAX; ++t) {
+              if (t < TA) {
+                const float xv = xin[(((int64_t)t * d.B + b) * Cin + ci) * plane + (int64_t)iy * d.W_in + ix];
+                acc[t] = fmaf(xv, wv, acc[t]);
+              }
+            }
+          }
+        }
+      }
+    }
+
+    const float sc = p.scale[co], sh = p.shift[co];
+    if (d.out_kind == SD_OUT_LIF) {
+      const int64_t orow = gout.row(b, oy, ox);
+      const int64_t vidx = ((int64_t)(co >> 3) * gout.R_alloc + orow) * 8 + (co & 7);
+      float v = p.v ? p.v[vidx] : (d.hard_reset ? d.v_reset : 0.f);
+      float cnt = 0.f;
+      __half* outp = (__half*)p.out;
+#pragma unroll
+      for (int t = 0; t < TMAX; ++t) {
+        if (t < T) {
+          const float x = fmaf(acc[TA == 1 ? 0 : t], sc, sh);
+          float h;
+          if (d.hard_reset) h = __fadd_rn(v, __fdiv_rn(__fsub_rn(x, __fsub_rn(v, d.v_reset)), d.tau));
+          else              h = __fadd_rn(v, __fdiv_rn(__fsub_rn(x, v), d.tau));
+          const bool s = h >= d.v_threshold;
+          v = d.hard_reset ? (s ? d.v_reset : h) : (s ? __fsub_rn(h, d.v_threshold) : h);
+          cnt += s ? 1.f : 0.f;
+          outp[gout.at(t, Cout8, co, orow)] = __float2half_rn(s ? 1.f : 0.f);
+        }
+      }
+      if (p.v) p.v[vidx] = v;
+      if (p.out_sum) p.out_sum[gout.at(0, Cout8, co, orow)] = __float2half_rn(cnt);
+    } else if (d.out_kind == SD_OUT_REAL_SEQ) {
+      float* outp = (float*)p.out;
+      const int64_t plane = (int64_t)d.H_out * d.W_out;
+#pragma unroll
+      for (int t = 0; t < TMAX; ++t)
+        if (t < T)
+          outp[(((int64_t)t * d.B + b) * Cout + co) * plane + (int64_t)oy * d.W_out + ox] =
+              fmaf(acc[TA == 1 ? 0 : t], sc, sh);
+    } else if (d.out_kind == SD_OUT_MEMOUT_TANH) {
+      float m = 0.f;
+#pragma unroll
+      for (int t = 0; t < TMAX; ++t)
+        if (t < T) m = __fadd_rn(m, __fmul_rn(fmaf(acc[TA == 1 ? 0 : t], sc, sh), p.coef.c[t]));
+      ((float*)p.out)[(((int64_t)b * Cout + co) * d.H_out + oy) * d.W_out + ox] = tanhf(m);
+    } else {  // SD_OUT_MEAN_T
+      float m = 0.f;
+      if (TA == 1 && d.in_kind == SD_IN_STF) {
+        // input already summed over T: sum_t (conv_t + bias) = conv(sum_t s_t) + T * bias
+        m = fmaf(acc[0], sc, __fmul_rn(sh, (float)T));
+      } else {
+#pragma unroll
+        for (int t = 0; t < TMAX; ++t)
+          if (t < T) m = __fadd_rn(m, fmaf(acc[TA == 1 ? 0 : t], sc, sh));
+      }
+      ((float*)p.out)[(((int64_t)b * d.H_out + oy) * d.W_out + ox) * Cout + co] = __fdiv_rn(m, (float)T);
+    }
+  }
+}
+
+// w (reference layout) -> [tap][ci][co]
+__global__ void pack_simt_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int kh,
+                                 int kw, int transposed) {
+  const int64_t total = (int64_t)kh * kw * Cin * Cout;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int co = (int)(i % Cout);
+    int64_t r = i / Cout;
+    int ci = (int)(r % Cin);
+    int tap = (int)(r / Cin);
+    int ky = tap / kw, kx = tap % kw;
+    int64_t src = transposed ? ((((int64_t)ci * Cout + co) * kh + ky) * kw + kx)
+                             : ((((int64_t)co * Cin + ci) * kh + ky) * kw + kx);
+    out[i] = w[src];
+  }
+}
+
+int validate_conv_desc(const sd_conv_desc* d) {
+  SD_REQUIRE(d != nullptr, "null descriptor");
+  SD_REQUIRE(d->T >= 1 && d->T <= SD_MAX_T, "conv: T=%d out of range [1,%d]", d->T, SD_MAX_T);
+  SD_REQUIRE(d->B >= 1 && d->C_in >= 1 && d->C_out >= 1 && d->H_in >= 1 && d->W_in >= 1 && d->H_out >= 1 &&
+                 d->W_out >= 1, "conv: non-positive dimension");
+  SD_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->stride >= 1 && d->pad >= 0, "conv: bad kernel/stride/padding");
+  SD_REQUIRE(d->in_kind >= SD_IN_REAL_CONST && d->in_kind <= SD_IN_STF, "conv: bad in_kind %d", d->in_kind);
+  SD_REQUIRE(d->out_kind >= SD_OUT_LIF && d->out_kind <= SD_OUT_MEAN_T, "conv: bad out_kind %d", d->out_kind);
+  if (d->in_kind == SD_IN_STF) {
+    SD_REQUIRE(d->in_T == d->T || d->in_T == 1, "conv: in_T must be T or 1");
+    SD_REQUIRE(d->C_in0 >= 1 && d->C_in0 <= d->C_in, "conv: C_in0 out of range");
+    SD_REQUIRE(d->C_in0 == d->C_in || d->C_in0 % 8 == 0, "conv: concat boundary must be a multiple of 8");
+  }
+  if (d->out_kind == SD_OUT_LIF) SD_REQUIRE(d->tau > 1.0f, "LIFNode requires tau > 1, got %f", (double)d->tau);
+  // output size consistent with torch's formulas (nn.Conv2d / nn.ConvTranspose2d docs)
+  if (!d->transposed) {
+    SD_REQUIRE(d->H_out == (d->H_in + 2 * d->pad - d->kh) / d->stride + 1 &&
+                   d->W_out == (d->W_in + 2 * d->pad - d->kw) / d->stride + 1, "conv: output size mismatch");
+  } else {
+    int h0 = (d->H_in - 1) * d->stride - 2 * d->pad + d->kh, w0 = (d->W_in - 1) * d->stride - 2 * d->pad + d->kw;
+    SD_REQUIRE(d->H_out >= h0 && d->H_out < h0 + d->stride && d->W_out >= w0 && d->W_out < w0 + d->stride,
+               "conv_transpose: output size mismatch (output_padding must be < stride)");
+  }
+  return SD_OK;
+}
+
+}  // namespace sd
+
+using namespace sd;
+
+extern "C" {
+
+int64_t sd_conv_weight_bytes_simt(const sd_conv_desc* d) {
+  if (!d) return 0;
+  return (int64_t)d->kh * d->kw * d->C_in * d->C_out * (int64_t)sizeof(float);
+}
+
+int sd_conv_pack_weights_simt(const sd_conv_desc* d, const float* w, void* packed, void* stream) {
+  int rc = validate_conv_desc(d);
+  if (rc) return rc;
+  SD_REQUIRE(w && packed, "null pointer argument");
+  SD_DEVICE_OR_RETURN();
+  int64_t n = (int64_t)d->kh * d->kw * d->C_in * d->C_out;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+  pack_simt_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(w, (float*)packed, d->C_out, d->C_in, d->kh,
+                                                                    d->kw, d->transposed);
+  SD_LAUNCH_CHECK();
+  return SD_OK;
+}
+
+int sd_conv_lif_simt(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
+  int rc = validate_conv_desc(d);
+  if (rc) return rc;
+  SD_REQUIRE(a && a->in && a->weights && a->scale && a->shift && a->out, "null pointer argument");
+  if (d->in_kind == SD_IN_STF && d->C_in0 < d->C_in) SD_REQUIRE(a->in2 != nullptr, "conv: in2 missing for concat");
+  if (d->out_kind == SD_OUT_MEMOUT_TANH) SD_REQUIRE(a->memout_coef_host != nullptr, "conv: memout_coef_host missing");
+  SD_DEVICE_OR_RETURN();
+  SimtParams p;
+  p.d = *d;
+  p.in = a->in; p.in2 = a->in2; p.w = (const float*)a->weights; p.scale = a->scale; p.shift = a->shift;
+  p.v = a->v; p.out = a->out; p.out_sum = (__half*)a->out_sum;
+  for (int t = 0; t < SD_MAX_T; ++t)
+    p.coef.c[t] = (a->memout_coef_host && t < d->T) ? a->memout_coef_host[t] : 0.f;
+  p.decay_keep = 0.f;
+  int64_t n = (int64_t)d->B * d->H_out * d->W_out * d->C_out;
+  int64_t blocks = (n + 255) / 256;
+  int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = as_stream(stream);
+  // TMAX bounds both the accumulator array and the unrolled epilogue; pick the smallest that fits T.
+  if (d->T <= 4) conv_simt_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(p);
+  else if (d->T <= 8) conv_simt_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(p);
+  else if (d->T <= 16) conv_simt_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(p);
+  else conv_simt_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(p);
+  SD_LAUNCH_CHECK();
+  return SD_OK;
+}
+
+}  // extern "C"

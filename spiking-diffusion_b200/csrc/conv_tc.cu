@@ -1,0 +1,595 @@
+// Fused 3x3 conv -> BatchNorm -> multi-step LIF as ONE tcgen05 implicit-GEMM kernel (sm_100a).
+//
+// Replaces layer.Conv2d -> layer.BatchNorm2d -> neuron.LIFNode for the spike->spike layers of the denoiser
+// (R/snn_model/vq_diffusion.py:165-187 via SJ/activation_based/layer.py:164-173,458-465 and neuron.py:799-809),
+// which carry >99.9 % of the sampling FLOPs.
+//
+// GEMM view.  Activations live in the STF layout (include/sd_b200.h): per timestep and per 8-channel chunk a
+// plane of 16-byte rows, rows = zero-padded pixel grid flattened (Wp = W+1 columns, one shared zero row between
+// images).  For that layout the 3x3/stride-1/pad-1 convolution is nine GEMMs whose A operands are the SAME rows
+// shifted by dy*Wp + dx.  In shared memory the planes are exactly the tcgen05 "no-swizzle, K-major" canonical
+// layout (core matrix = 8 rows x 16 B contiguous, SBO = 128 B between 8-row groups, LBO = plane stride between
+// 8-channel chunks), so a tap is just a different 16-byte-aligned start address in the A descriptor: the input
+// tile is loaded ONCE per K-block and reused by all 9 taps (9x less L2->SMEM traffic than im2col).
+//
+//   M tile  = 128 consecutive padded rows (2 images of a 7x7 grid), all T timesteps
+//   N tile  = 32..128 output channels
+//   K block = 16..64 input channels, x 9 taps, x nsplit fp16 weight terms
+//   D       = T accumulators of [128 x N] fp32 resident in TMEM (T*N <= 512 columns, x2 stages when they fit)
+//
+// Exactness.  Spikes (and T-summed spike counts) are exact in fp16.  Each fp32 weight is scaled by an exact
+// per-output-channel power of two and split into nsplit fp16 terms (hi, lo = 22 significant bits for
+// nsplit = 2); every product is exact and accumulation is fp32 in the tensor core.  Both terms accumulate into
+// the same TMEM accumulator (the A tile is shared, only the B descriptor changes).
+//
+// Warp roles (384 threads, 1 CTA / SM, persistent over tiles):
+//   warps 0-7  epilogue: tcgen05.ld -> BN affine -> LIF over all T in registers -> fp16 spikes / T-sum / v
+//   warp  8    A producer  (cp.async.bulk global -> shared, one copy per (t, chunk) plane, mbarrier tx)
+//   warp  9    B producer  (cp.async.bulk of one pre-packed [split][chunk][n][8] weight block per tap)
+//   warp 10    MMA issuer  (one lane issues tcgen05.mma, tcgen05.commit releases stages)
+//   warp 11    TMEM allocator
+#include <stdlib.h>
+#include "common.cuh"
+
+namespace sd {
+
+constexpr int kTcThreads = 384;
+constexpr int kMaxAStages = 4;
+constexpr int kMaxBStages = 8;
+constexpr uint32_t kSmemBudget = 220 * 1024;
+
+struct TcConfig {
+  int T_acc;       // accumulators per tile (T for LIF, 1 for the T-summed linear read-out)
+  int N_TILE;
+  int KBLK;        // input channels per K block
+  int acc_stages;
+  int a_stages, b_stages;
+  int halo, rows_ld;
+  uint32_t a_stage_bytes, b_stage_bytes, smem_bytes;
+  int n_tiles, m_tiles, num_kblocks, c0_blocks;
+};
+
+struct TcParams {
+  const __half* in0;
+  const __half* in1;
+  const __half* wpack;
+  const float* scale;
+  const float* shift;
+  __half* out_spk;
+  __half* out_sum;
+  float* out_real;
+  float* v;
+  int64_t R_alloc, G, R_valid;
+  int C8_0, C8_1, Cout, Cout8;
+  int T, H, W, Wp, P;
+  int nsplit, out_kind, hard_reset;
+  float tau, v_th, v_reset;
+  uint32_t idesc;
+  TcConfig c;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor field layout):
+//   [0,14) start >> 4 | [16,30) LBO >> 4 | [32,46) SBO >> 4 | [46,48) version = 1 | [61,64) layout = 0 (none)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         ((uint64_t)1 << 46);
+}
+
+struct PipeState {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int n) {
+    if (++stage == n) { stage = 0; phase ^= 1; }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Kernel
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const TcConfig& c = p.c;
+  // barrier block (first 256 B), then A stages, then B stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (kMaxAStages + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + kMaxBStages + s); };
+  auto acc_full = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages + s); };
+  auto acc_empty = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages + 2 + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxAStages + 2 * kMaxBStages + 4));
+  const uint32_t a_base = smem_u32(smem + 1024);
+  const uint32_t b_base = a_base + c.a_stages * c.a_stage_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < c.a_stages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < c.b_stages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 11) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = c.m_tiles * c.n_tiles;
+  const int chunks = c.KBLK >> 3;            // 8-channel chunks per K block
+  const uint32_t plane_bytes = (uint32_t)c.rows_ld * 16u;
+
+  if (warp == 8) {
+    // ===== A producer =====
+    PipeState st;
+    const int ncopy = c.T_acc * chunks;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int64_t row0 = (int64_t)(tile / c.n_tiles) * kTileRows;
+      for (int kb = 0; kb < c.num_kblocks; ++kb) {
+        if (lane == 0) {
+          mbar_wait(a_empty(st.stage), st.phase ^ 1);
+          mbar_expect_tx(a_full(st.stage), c.a_stage_bytes);
+        }
+        __syncwarp();
+        const bool seg1 = kb >= c.c0_blocks;
+        const __half* src = seg1 ? p.in1 : p.in0;
+        const int C8 = seg1 ? p.C8_1 : p.C8_0;
+        const int chunk0 = (seg1 ? kb - c.c0_blocks : kb) * chunks;
+        for (int i = lane; i < ncopy; i += 32) {
+          const int t = i / chunks, ch = i - t * chunks;
+          const __half* g = src + ((((int64_t)t * C8 + chunk0 + ch) * p.R_alloc) + p.G + row0 - c.halo) * 8;
+          bulk_g2s(a_base + st.stage * c.a_stage_bytes + (uint32_t)i * plane_bytes, g, plane_bytes, a_full(st.stage));
+        }
+        st.advance(c.a_stages);
+      }
+    }
+  } else if (warp == 9) {
+    // ===== B producer =====
+    if (lane == 0) {
+      PipeState st;
+      const int64_t stage_halfs = c.b_stage_bytes / 2;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % c.n_tiles;
+        const __half* wsrc = p.wpack + (int64_t)n_tile * c.num_kblocks * 9 * stage_halfs;
+        for (int it = 0; it < c.num_kblocks * 9; ++it) {
+          mbar_wait(b_empty(st.stage), st.phase ^ 1);
+          mbar_expect_tx(b_full(st.stage), c.b_stage_bytes);
+          bulk_g2s(b_base + st.stage * c.b_stage_bytes, wsrc + (int64_t)it * stage_halfs, c.b_stage_bytes,
+                   b_full(st.stage));
+          st.advance(c.b_stages);
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      PipeState sa, sb, sc;
+      const uint32_t b_split_bytes = (uint32_t)chunks * c.N_TILE * 16u;
+      const uint32_t b_lbo = (uint32_t)c.N_TILE * 16u;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(acc_empty(sc.stage), sc.phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)(sc.stage * c.T_acc * c.N_TILE);
+        for (int kb = 0; kb < c.num_kblocks; ++kb) {
+          mbar_wait(a_full(sa.stage), sa.phase);
+          tc_fence_after();
+          const uint32_t a_stage = a_base + sa.stage * c.a_stage_bytes;
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(b_full(sb.stage), sb.phase);
+            tc_fence_after();
+            const uint32_t b_stage = b_base + sb.stage * c.b_stage_bytes;
+            const int shift = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
+            const uint32_t a_row_off = (uint32_t)(c.halo + shift) * 16u;
+            for (int t = 0; t < c.T_acc; ++t) {
+              for (int sp = 0; sp < p.nsplit; ++sp) {
+                for (int ks = 0; ks < (c.KBLK >> 4); ++ks) {
+                  const uint64_t adesc =
+                      make_desc(a_stage + (uint32_t)(t * chunks + 2 * ks) * plane_bytes + a_row_off, plane_bytes, 128);
+                  const uint64_t bdesc = make_desc(b_stage + sp * b_split_bytes + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128);
+                  const uint32_t accum = (kb | tap | sp | ks) != 0 ? 1u : 0u;
+                  tc_mma_f16(d_base + (uint32_t)(t * c.N_TILE), adesc, bdesc, p.idesc, accum);
+                }
+              }
+            }
+            tc_commit(b_empty(sb.stage));
+            sb.advance(c.b_stages);
+          }
+          tc_commit(a_empty(sa.stage));
+          sa.advance(c.a_stages);
+        }
+        tc_commit(acc_full(sc.stage));
+        sc.advance(c.acc_stages);
+      }
+    }
+  } else if (warp < 8) {
+    // ===== epilogue =====
+    PipeState sc;
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int col_lo = (warp >> 2) * (c.N_TILE >> 1);
+    const int col_hi = col_lo + (c.N_TILE >> 1);
+    const float inv_T = 1.0f / (float)p.T;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n0 = (tile % c.n_tiles) * c.N_TILE;
+      const int64_t r = (int64_t)(tile / c.n_tiles) * kTileRows + q * 32 + lane;  // padded row (without guard)
+      const int pp = (int)(r % p.P);
+      const int py = pp / p.Wp, px = pp - py * p.Wp;
+      const bool valid = (r < p.R_valid) && (px < p.W) && (py < p.H);
+      mbar_wait(acc_full(sc.stage), sc.phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc.stage * c.T_acc * c.N_TILE);
+      for (int cc = col_lo; cc < col_hi; cc += 16) {
+        const int n = n0 + cc;  // first output channel of this 16-column group (warp-uniform)
+        if (n >= p.Cout) continue;  // zero-padded tail of the last N tile
+        float sc_[16], sh_[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(p.scale + n + j));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.shift + n + j));
+          sc_[j] = a.x; sc_[j + 1] = a.y; sc_[j + 2] = a.z; sc_[j + 3] = a.w;
+          sh_[j] = b.x; sh_[j + 1] = b.y; sh_[j + 2] = b.z; sh_[j + 3] = b.w;
+        }
+        if (p.out_kind == SD_OUT_LIF) {
+          float v[16], cnt[16];
+          const int64_t vrow = ((int64_t)(n >> 3) * p.R_alloc + p.G + r) * 8;  // chunk n/8; next chunk + R_alloc*8
+          if (p.v != nullptr && valid && n < p.Cout) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float4 a = *reinterpret_cast<const float4*>(p.v + vrow + (int64_t)h * p.R_alloc * 8);
+              const float4 b = *reinterpret_cast<const float4*>(p.v + vrow + (int64_t)h * p.R_alloc * 8 + 4);
+              v[8 * h] = a.x; v[8 * h + 1] = a.y; v[8 * h + 2] = a.z; v[8 * h + 3] = a.w;
+              v[8 * h + 4] = b.x; v[8 * h + 5] = b.y; v[8 * h + 6] = b.z; v[8 * h + 7] = b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = p.hard_reset ? p.v_reset : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) cnt[j] = 0.f;
+          for (int t = 0; t < c.T_acc; ++t) {
+            uint32_t acc[16];
+            tc_ld16(t_base + (uint32_t)(t * c.N_TILE + cc), acc);
+            tc_ld_wait();
+            uint32_t packed[8];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float x = fmaf(__uint_as_float(acc[j]), sc_[j], sh_[j]);
+              float h;
+              if (p.hard_reset) h = __fadd_rn(v[j], __fdiv_rn(__fsub_rn(x, __fsub_rn(v[j], p.v_reset)), p.tau));
+              else              h = __fadd_rn(v[j], __fdiv_rn(__fsub_rn(x, v[j]), p.tau));
+              const bool s = h >= p.v_th;
+              v[j] = p.hard_reset ? (s ? p.v_reset : h) : (s ? __fsub_rn(h, p.v_th) : h);
+              cnt[j] += s ? 1.f : 0.f;
+              const uint32_t bits = s ? 0x3C00u : 0u;  // fp16 1.0
+              if (j & 1) packed[j >> 1] |= bits << 16; else packed[j >> 1] = bits;
+            }
+            if (valid && n < p.Cout && p.out_spk != nullptr) {
+              __half* o = p.out_spk + (((int64_t)t * p.Cout8 + (n >> 3)) * p.R_alloc + p.G + r) * 8;
+              *reinterpret_cast<uint4*>(o) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+              *reinterpret_cast<uint4*>(o + p.R_alloc * 8) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            }
+          }
+          if (valid && n < p.Cout) {
+            if (p.out_sum != nullptr) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const __half2 h2 = __floats2half2_rn(cnt[j], cnt[j + 1]);
+                pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+              }
+              __half* o = p.out_sum + ((int64_t)(n >> 3) * p.R_alloc + p.G + r) * 8;
+              *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(o + p.R_alloc * 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+            if (p.v != nullptr) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                float* o = p.v + vrow + (int64_t)h * p.R_alloc * 8;
+                *reinterpret_cast<float4*>(o) = make_float4(v[8 * h], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]);
+              }
+            }
+          }
+        } else {
+          // SD_OUT_MEAN_T on a T-summed input: (conv(sum_t s_t) * scale + T * shift) / T, channels-last fp32
+          uint32_t acc[16];
+          tc_ld16(t_base + (uint32_t)cc, acc);
+          tc_ld_wait();
+          if (valid && n < p.Cout) {
+            const int64_t img = r / p.P;
+            float* o = p.out_real + ((img * p.H + py) * p.W + px) * (int64_t)p.Cout + n;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 y;
+              y.x = __fmul_rn(fmaf(__uint_as_float(acc[j]), sc_[j], __fmul_rn(sh_[j], (float)p.T)), inv_T);
+              y.y = __fmul_rn(fmaf(__uint_as_float(acc[j + 1]), sc_[j + 1], __fmul_rn(sh_[j + 1], (float)p.T)), inv_T);
+              y.z = __fmul_rn(fmaf(__uint_as_float(acc[j + 2]), sc_[j + 2], __fmul_rn(sh_[j + 2], (float)p.T)), inv_T);
+              y.w = __fmul_rn(fmaf(__uint_as_float(acc[j + 3]), sc_[j + 3], __fmul_rn(sh_[j + 3], (float)p.T)), inv_T);
+              *reinterpret_cast<float4*>(o + j) = y;
+            }
+          }
+        }
+      }
+      // release the accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(sc.stage));
+      sc.advance(c.acc_stages);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 11) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Configuration (shared by weight packing and launch)
+// ---------------------------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+static int tc_supported(const sd_conv_desc* d, const char** why) {
+  *why = "";
+  if (d->transposed || d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != 1) { *why = "only 3x3 stride 1 pad 1"; return 0; }
+  if (d->in_kind != SD_IN_STF) { *why = "input must be STF spikes"; return 0; }
+  if (d->H_in != d->H_out || d->W_in != d->W_out) { *why = "output grid must equal input grid"; return 0; }
+  if (d->out_kind != SD_OUT_LIF && d->out_kind != SD_OUT_MEAN_T) { *why = "out_kind must be LIF or MEAN_T"; return 0; }
+  if (d->out_kind == SD_OUT_LIF && (d->in_T != d->T || d->T > 16)) { *why = "LIF needs in_T == T <= 16"; return 0; }
+  if (d->out_kind == SD_OUT_MEAN_T && d->in_T != 1) { *why = "MEAN_T needs a T-summed input (in_T == 1)"; return 0; }
+  const int c0 = d->C_in0, c1 = d->C_in - d->C_in0;
+  if (c0 % 16 || c1 % 16) { *why = "channel segments must be multiples of 16"; return 0; }
+  if (d->C_out % 16) { *why = "C_out must be a multiple of 16"; return 0; }
+  if (d->nsplit < 1 || d->nsplit > 2) { *why = "nsplit must be 1 or 2"; return 0; }
+  if (d->W_in + 2 > 64) { *why = "grid too wide for the row-shift window"; return 0; }
+  return 1;
+}
+
+static int tc_config(const sd_conv_desc* d, TcConfig* c) {
+  const char* why;
+  if (!tc_supported(d, &why)) { set_error("conv_tc: unsupported descriptor: %s", why); return SD_ERR_UNSUPPORTED; }
+  c->T_acc = d->out_kind == SD_OUT_LIF ? d->T : 1;
+  int n_tile;
+  if (c->T_acc * 128 * 2 <= 512) n_tile = 128;
+  else if (c->T_acc * 64 <= 512) n_tile = 64;
+  else n_tile = 32;
+  n_tile = env_int("SD_TC_NTILE", n_tile);
+  while (n_tile > 32 && n_tile / 2 >= d->C_out) n_tile /= 2;
+  if (!(n_tile == 32 || n_tile == 64 || n_tile == 128) || c->T_acc * n_tile > 512) {
+    set_error("conv_tc: bad N tile %d for T=%d", n_tile, c->T_acc);
+    return SD_ERR_UNSUPPORTED;
+  }
+  c->N_TILE = n_tile;
+  c->acc_stages = 512 / (c->T_acc * n_tile) >= 2 ? 2 : 1;
+  c->acc_stages = env_int("SD_TC_ACC_STAGES", c->acc_stages) >= 2 && 512 / (c->T_acc * n_tile) >= 2 ? 2 : 1;
+  c->halo = d->W_in + 2;
+  c->rows_ld = kTileRows + 2 * c->halo;
+  const int c0 = d->C_in0, c1 = d->C_in - d->C_in0;
+  int kblk = env_int("SD_TC_KBLK", 32);
+  for (;; kblk /= 2) {
+    if (kblk < 16) { set_error("conv_tc: no K block fits shared memory"); return SD_ERR_UNSUPPORTED; }
+    if (!(kblk == 16 || kblk == 32 || kblk == 64)) continue;
+    if (c0 % kblk || c1 % kblk) continue;
+    c->a_stage_bytes = (uint32_t)c->T_acc * (kblk / 8) * c->rows_ld * 16;
+    c->b_stage_bytes = (uint32_t)d->nsplit * (kblk / 8) * n_tile * 16;
+    if (2 * c->a_stage_bytes + 3 * c->b_stage_bytes + 1024 <= kSmemBudget) break;
+  }
+  c->KBLK = kblk;
+  // split the budget: B ring of 4 (one tap each), the rest to A (2..4 K blocks in flight)
+  c->b_stages = 4;
+  while (c->b_stages > 3 && 2 * c->a_stage_bytes + c->b_stages * c->b_stage_bytes + 1024 > kSmemBudget) --c->b_stages;
+  c->a_stages = (int)((kSmemBudget - 1024 - c->b_stages * c->b_stage_bytes) / c->a_stage_bytes);
+  if (c->a_stages > kMaxAStages) c->a_stages = kMaxAStages;
+  uint32_t left = kSmemBudget - 1024 - c->a_stages * c->a_stage_bytes;
+  c->b_stages = (int)(left / c->b_stage_bytes);
+  if (c->b_stages > kMaxBStages) c->b_stages = kMaxBStages;
+  c->smem_bytes = 1024 + c->a_stages * c->a_stage_bytes + c->b_stages * c->b_stage_bytes;
+  c->n_tiles = (d->C_out + n_tile - 1) / n_tile;
+  const int64_t R = (int64_t)d->B * (d->H_in + 1) * (d->W_in + 1);
+  c->m_tiles = (int)((R + kTileRows - 1) / kTileRows);
+  c->c0_blocks = c0 / kblk;
+  c->num_kblocks = c0 / kblk + c1 / kblk;
+  return SD_OK;
+}
+
+// ---- weight packing -------------------------------------------------------------------------------
+// exponent e[co] such that max|w[co]| * 2^e lies in [2^13, 2^14); chan_scale = 2^-e
+__global__ void tc_chan_exp_kernel(const float* __restrict__ w, int Cin, float* __restrict__ chan_scale, int* __restrict__ e_out) {
+  const int co = blockIdx.x;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < Cin * 9; i += blockDim.x) m = fmaxf(m, fabsf(w[(int64_t)co * Cin * 9 + i]));
+  __shared__ float red[256];
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int e = 0;
+    if (red[0] > 0.f && isfinite(red[0])) {
+      int ex;
+      frexpf(red[0], &ex);  // red = f * 2^ex, f in [0.5, 1)  ->  red * 2^(14 - ex) in [2^13, 2^14)
+      e = 14 - ex;
+    }
+    e_out[co] = e;
+    chan_scale[co] = ldexpf(1.0f, -e);
+  }
+}
+
+__global__ void tc_pack_kernel(const float* __restrict__ w, const int* __restrict__ e_in, __half* __restrict__ out,
+                               int Cout, int Cin, int N_TILE, int KBLK, int nsplit, int n_tiles, int num_kblocks) {
+  const int chunks = KBLK / 8;
+  const int64_t total = (int64_t)n_tiles * num_kblocks * 9 * nsplit * chunks * N_TILE * 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int j = (int)(i % 8);
+    int64_t r = i / 8;
+    int n = (int)(r % N_TILE); r /= N_TILE;
+    int ch = (int)(r % chunks); r /= chunks;
+    int sp = (int)(r % nsplit); r /= nsplit;
+    int tap = (int)(r % 9); r /= 9;
+    int kb = (int)(r % num_kblocks);
+    int nt = (int)(r / num_kblocks);
+    const int co = nt * N_TILE + n;
+    const int ci = kb * KBLK + ch * 8 + j;
+    float val = 0.f;
+    if (co < Cout) {
+      const float ws = ldexpf(w[((int64_t)co * Cin + ci) * 9 + tap], e_in[co]);  // exact power-of-two scaling
+      const __half hi = __float2half_rn(ws);
+      val = sp == 0 ? __half2float(hi) : __fsub_rn(ws, __half2float(hi));
+    }
+    out[i] = __float2half_rn(val);
+  }
+}
+
+}  // namespace sd
+
+using namespace sd;
+
+extern "C" {
+
+int sd_conv_tc_supported(const sd_conv_desc* d) {
+  if (!d || validate_conv_desc(d) != SD_OK) return 0;
+  const char* why;
+  if (!tc_supported(d, &why)) return 0;
+  TcConfig c;
+  return tc_config(d, &c) == SD_OK ? 1 : 0;
+}
+
+int64_t sd_conv_weight_bytes_tc(const sd_conv_desc* d) {
+  TcConfig c;
+  if (!d || validate_conv_desc(d) != SD_OK || tc_config(d, &c) != SD_OK) return 0;
+  // + C_out ints of scratch for the per-channel exponents at the end
+  return (int64_t)c.n_tiles * c.num_kblocks * 9 * c.b_stage_bytes + (int64_t)d->C_out * 4;
+}
+
+int sd_conv_pack_weights_tc(const sd_conv_desc* d, const float* w, void* packed, float* chan_scale_out, void* stream) {
+  int rc = validate_conv_desc(d);
+  if (rc) return rc;
+  TcConfig c;
+  rc = tc_config(d, &c);
+  if (rc) return rc;
+  SD_REQUIRE(w && packed && chan_scale_out, "null pointer argument");
+  SD_DEVICE_OR_RETURN();
+  cudaStream_t st = as_stream(stream);
+  const int64_t main_bytes = (int64_t)c.n_tiles * c.num_kblocks * 9 * c.b_stage_bytes;
+  int* e_buf = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(packed) + main_bytes);
+  tc_chan_exp_kernel<<<d->C_out, 256, 0, st>>>(w, d->C_in, chan_scale_out, e_buf);
+  SD_LAUNCH_CHECK();
+  const int64_t total = main_bytes / 2;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+  tc_pack_kernel<<<(unsigned)blocks, 256, 0, st>>>(w, e_buf, (__half*)packed, d->C_out, d->C_in, c.N_TILE, c.KBLK,
+                                                   d->nsplit, c.n_tiles, c.num_kblocks);
+  SD_LAUNCH_CHECK();
+  return SD_OK;
+}
+
+int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
+  int rc = validate_conv_desc(d);
+  if (rc) return rc;
+  TcConfig c;
+  rc = tc_config(d, &c);
+  if (rc) return rc;
+  SD_REQUIRE(a && a->in && a->weights && a->scale && a->shift && a->out, "null pointer argument");
+  if (d->C_in0 < d->C_in) SD_REQUIRE(a->in2 != nullptr, "conv_tc: in2 missing for concat");
+  SD_DEVICE_OR_RETURN();
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.in0 = (const __half*)a->in;
+  p.in1 = (const __half*)a->in2;
+  p.wpack = (const __half*)a->weights;
+  p.scale = a->scale;
+  p.shift = a->shift;
+  p.v = a->v;
+  if (d->out_kind == SD_OUT_LIF) { p.out_spk = (__half*)a->out; p.out_sum = (__half*)a->out_sum; }
+  else p.out_real = (float*)a->out;
+  StfGeom g(d->B, d->H_in, d->W_in);
+  p.R_alloc = g.R_alloc; p.G = g.G; p.R_valid = (int64_t)d->B * g.P;
+  p.C8_0 = d->C_in0 / 8; p.C8_1 = (d->C_in - d->C_in0) / 8;
+  p.Cout = d->C_out; p.Cout8 = c8(d->C_out);
+  p.T = d->T; p.H = d->H_in; p.W = d->W_in; p.Wp = g.Wp; p.P = g.P;
+  p.nsplit = d->nsplit; p.out_kind = d->out_kind; p.hard_reset = d->hard_reset;
+  p.tau = d->tau; p.v_th = d->v_threshold; p.v_reset = d->v_reset;
+  // cute::UMMA::InstrDescriptor: c_format F32 (bit 4), a/b F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+  p.idesc = (1u << 4) | ((uint32_t)(c.N_TILE >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
+  p.c = c;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SD_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int grid = c.m_tiles * c.n_tiles;
+  if (grid > sm_count()) grid = sm_count();
+  conv3x3_tc_kernel<<<grid, kTcThreads, c.smem_bytes, as_stream(stream)>>>(p);
+  SD_LAUNCH_CHECK();
+  return SD_OK;
+}
+
+}  // extern "C"

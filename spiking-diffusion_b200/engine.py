@@ -1,0 +1,362 @@
+"""Fused execution plans over the C-ABI (libsd_b200.so).
+
+A *plan* owns, for one fixed shape, the pre-packed weights, folded BatchNorm affine and the STF activation
+buffers of a chain of conv -> BN -> LIF layers, and enqueues one C-ABI call per layer on the current CUDA
+stream.  PyTorch is used for device memory and streams only.
+
+  FusedLayer     one conv[-BN][-LIF] stage (SIMT or tcgen05 implementation)
+  DenoiserPlan   DummyModel.forward            (R/snn_model/vq_diffusion.py:189-208)
+  SamplerPlan    AbsorbingDiffusion.sample     (R/snn_model/vq_diffusion.py:103-142)
+  VQVAEPlan      encoder / quantiser / generator / decoder of SNN_VQVAE (R/snn_model/vae_model.py:101-196)
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import ConvArgs, ConvDesc, check, lib, ptr, stream_ptr
+
+BN_EPS_DEFAULT = 1e-5
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must be a CUDA tensor: spiking_diffusion_b200 has no CPU path "
+                           "(the CPU oracle lives under oracle/ and is test infrastructure only)")
+
+
+def stf_empty(T: int, B: int, C: int, H: int, W: int, device) -> torch.Tensor:
+    """Zero-filled STF buffer (pad/guard rows must stay zero; kernels only write valid rows)."""
+    n = lib().sd_stf_bytes(T, B, C, H, W) // 2
+    return torch.zeros(n, dtype=torch.float16, device=device)
+
+
+def stf_from_nchw(x: torch.Tensor) -> torch.Tensor:
+    T, B, C, H, W = x.shape
+    out = torch.empty(lib().sd_stf_bytes(T, B, C, H, W) // 2, dtype=torch.float16, device=x.device)
+    check(lib().sd_stf_from_nchw(ptr(x.contiguous().float()), ptr(out), T, B, C, H, W, stream_ptr()))
+    return out
+
+
+def stf_to_nchw(stf: torch.Tensor, T: int, B: int, C: int, H: int, W: int) -> torch.Tensor:
+    out = torch.empty((T, B, C, H, W), dtype=torch.float32, device=stf.device)
+    check(lib().sd_stf_to_nchw(ptr(stf), ptr(out), T, B, C, H, W, stream_ptr()))
+    return out
+
+
+def fold_bn(conv_bias: Optional[torch.Tensor], c_out: int, bn, device):
+    """(scale, shift) with BN(conv_nobias(x) + b) = conv_nobias(x) * scale + shift, evaluated in float64.
+
+    SpikingJelly's own fold helper asserts ``conv.bias is None`` (SJ/activation_based/functional.py:731) while
+    every reference conv has a bias, so the fold is re-derived:
+    scale = gamma / sqrt(running_var + eps);  shift = (b - running_mean) * scale + beta.
+    """
+    b = torch.zeros(c_out, dtype=torch.float64, device=device) if conv_bias is None else conv_bias.detach().double()
+    if bn is None:
+        return torch.ones(c_out, dtype=torch.float32, device=device), b.float().contiguous()
+    inv = torch.rsqrt(bn.running_var.detach().double() + bn.eps)
+    gamma = bn.weight.detach().double() if bn.weight is not None else torch.ones_like(inv)
+    beta = bn.bias.detach().double() if bn.bias is not None else torch.zeros_like(inv)
+    scale = gamma * inv
+    shift = (b - bn.running_mean.detach().double()) * scale + beta
+    return scale.float().contiguous(), shift.float().contiguous()
+
+
+class FusedLayer:
+    """One conv[-BN][-LIF] stage bound to a fixed shape.  ``impl``: 'simt', 'tc' or 'auto'."""
+
+    def __init__(self, conv, bn, lif, *, T: int, B: int, H_in: int, W_in: int, in_kind: int, out_kind: int,
+                 impl: str = "auto", nsplit: int = 2, in_T: Optional[int] = None, C_in0: Optional[int] = None,
+                 memout_coef: Optional[torch.Tensor] = None):
+        L = lib()
+        w = conv.weight.detach()
+        _require_cuda(w, "layer weights")
+        transposed = isinstance(conv, torch.nn.ConvTranspose2d)
+        kh, kw = conv.kernel_size
+        stride, pad = conv.stride[0], conv.padding[0]
+        if conv.stride[0] != conv.stride[1] or conv.padding[0] != conv.padding[1]:
+            raise ValueError("only square stride/padding are supported")
+        if conv.dilation != (1, 1) or conv.groups != 1:
+            raise ValueError("dilation/groups other than 1 are not supported")
+        if transposed:
+            C_in, C_out = w.shape[0], w.shape[1]
+            op = conv.output_padding[0]
+            H_out = (H_in - 1) * stride - 2 * pad + kh + op
+            W_out = (W_in - 1) * stride - 2 * pad + kw + op
+        else:
+            C_out, C_in = w.shape[0], w.shape[1]
+            H_out = (H_in + 2 * pad - kh) // stride + 1
+            W_out = (W_in + 2 * pad - kw) // stride + 1
+        d = ConvDesc()
+        d.T, d.B, d.C_in, d.H_in, d.W_in = T, B, C_in, H_in, W_in
+        d.C_out, d.H_out, d.W_out = C_out, H_out, W_out
+        d.kh, d.kw, d.stride, d.pad, d.transposed = kh, kw, stride, pad, int(transposed)
+        d.in_kind, d.out_kind = in_kind, out_kind
+        d.in_T = (T if in_T is None else in_T) if in_kind == _lib.IN_STF else T
+        d.C_in0 = C_in if C_in0 is None else C_in0
+        if lif is not None:
+            d.tau, d.v_threshold = float(lif.tau), float(lif.v_threshold)
+            d.hard_reset = int(lif.v_reset is not None)
+            d.v_reset = float(lif.v_reset) if lif.v_reset is not None else 0.0
+            if not getattr(lif, "decay_input", True):
+                raise ValueError("fused layers implement decay_input=True (the reference's setting)")
+        else:
+            d.tau, d.v_threshold, d.v_reset, d.hard_reset = 2.0, 1.0, 0.0, 1
+        d.nsplit = nsplit
+        self.desc = d
+        self.device = w.device
+        self.T, self.B, self.C_in, self.C_out = T, B, C_in, C_out
+        self.H_in, self.W_in, self.H_out, self.W_out = H_in, W_in, H_out, W_out
+        if impl == "auto":
+            impl = "tc" if L.sd_conv_tc_supported(ctypes.byref(d)) else "simt"
+        if impl == "tc" and not L.sd_conv_tc_supported(ctypes.byref(d)):
+            raise ValueError("layer is not supported by the tcgen05 kernel: " + L.sd_last_error().decode())
+        self.impl = impl
+        scale, shift = fold_bn(conv.bias, C_out, bn, self.device)
+        wsrc = w.float().contiguous()
+        if impl == "tc":
+            nbytes = L.sd_conv_weight_bytes_tc(ctypes.byref(d))
+            self.wpack = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            chan = torch.empty(C_out, dtype=torch.float32, device=self.device)
+            check(L.sd_conv_pack_weights_tc(ctypes.byref(d), ptr(wsrc), ptr(self.wpack), ptr(chan), stream_ptr()))
+            scale = (scale.double() * chan.double()).float().contiguous()  # exact: chan is a power of two
+        else:
+            nbytes = L.sd_conv_weight_bytes_simt(ctypes.byref(d))
+            self.wpack = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            check(L.sd_conv_pack_weights_simt(ctypes.byref(d), ptr(wsrc), ptr(self.wpack), stream_ptr()))
+        self.scale, self.shift = scale, shift
+        self._coef = None
+        if out_kind == _lib.OUT_MEMOUT_TANH:
+            if memout_coef is None:
+                raise ValueError("memout_coef required for the memout+tanh tail")
+            self._coef = (ctypes.c_float * T)(*[float(v) for v in memout_coef.detach().reshape(-1).cpu().tolist()[:T]])
+        self._fn = L.sd_conv_lif_tc if impl == "tc" else L.sd_conv_lif_simt
+
+    def flops(self) -> int:
+        """Dense algorithmic FLOPs (2*MAC) of one call, counted as SURVEY.md section 8(d) does."""
+        d = self.desc
+        if d.transposed:
+            mac = d.C_in * d.C_out * d.kh * d.kw * d.H_in * d.W_in
+        else:
+            mac = d.C_in * d.C_out * d.kh * d.kw * d.H_out * d.W_out
+        return 2 * mac * d.B * d.T
+
+    def alloc_out(self) -> torch.Tensor:
+        d = self.desc
+        if d.out_kind == _lib.OUT_LIF:
+            return stf_empty(d.T, d.B, d.C_out, d.H_out, d.W_out, self.device)
+        if d.out_kind == _lib.OUT_REAL_SEQ:
+            return torch.empty((d.T, d.B, d.C_out, d.H_out, d.W_out), dtype=torch.float32, device=self.device)
+        if d.out_kind == _lib.OUT_MEMOUT_TANH:
+            return torch.empty((d.B, d.C_out, d.H_out, d.W_out), dtype=torch.float32, device=self.device)
+        return torch.empty((d.B, d.H_out, d.W_out, d.C_out), dtype=torch.float32, device=self.device)
+
+    def alloc_sum(self) -> torch.Tensor:
+        d = self.desc
+        return stf_empty(1, d.B, d.C_out, d.H_out, d.W_out, self.device)
+
+    def alloc_state(self) -> torch.Tensor:
+        """LIF membrane state in the planar layout [C_out/8][R_alloc][8] fp32, initialised to v_reset."""
+        d = self.desc
+        n = lib().sd_stf_bytes(1, d.B, d.C_out, d.H_out, d.W_out) // 2
+        return torch.full((n,), d.v_reset if d.hard_reset else 0.0, dtype=torch.float32, device=self.device)
+
+    def run(self, x: torch.Tensor, out: torch.Tensor, x2: Optional[torch.Tensor] = None,
+            out_sum: Optional[torch.Tensor] = None, v: Optional[torch.Tensor] = None) -> torch.Tensor:
+        a = ConvArgs()
+        a.in_, a.in2, a.weights = ptr(x), ptr(x2), ptr(self.wpack)
+        a.scale, a.shift, a.v = ptr(self.scale), ptr(self.shift), ptr(v)
+        a.out, a.out_sum = ptr(out), ptr(out_sum)
+        a.memout_coef_host = ctypes.cast(self._coef, ctypes.c_void_p) if self._coef is not None else None
+        check(self._fn(ctypes.byref(self.desc), ctypes.byref(a), stream_ptr()))
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+class DenoiserPlan:
+    """DummyModel.forward for a fixed (T, b, h, w): conv1 (real, constant over T) on CUDA cores, conv2..conv5 as
+    fused tcgen05 conv+BN+LIF, conv6 on the T-summed spikes of cat(x5, x1) (linear read-out, mean over T)."""
+
+    def __init__(self, model, T: int, b: int, h: int, w: int, nsplit: int = 2, impl: str = "auto"):
+        dev = model.conv1[0].weight.device
+        _require_cuda(model.conv1[0].weight, "DummyModel parameters")
+        self.T, self.b, self.h, self.w, self.K = T, b, h, w, model.num_embeddings
+        self.device = dev
+        mk = lambda seq, **kw: FusedLayer(seq[0], seq[1] if len(seq) > 1 else None, seq[2] if len(seq) > 2 else None,
+                                          T=T, B=b, H_in=h, W_in=w, nsplit=nsplit, **kw)
+        self.l1 = mk(model.conv1, in_kind=_lib.IN_REAL_CONST, out_kind=_lib.OUT_LIF, impl="simt")
+        self.l2 = mk(model.conv2, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
+        self.l3 = mk(model.conv3, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
+        self.l4 = mk(model.conv4, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
+        self.l5 = mk(model.conv5, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
+        self.l6 = mk(model.conv6, in_kind=_lib.IN_STF, out_kind=_lib.OUT_MEAN_T, impl=impl, in_T=1,
+                     C_in0=self.l5.C_out)
+        self.layers = [self.l1, self.l2, self.l3, self.l4, self.l5, self.l6]
+        self.xin = torch.empty((b, 2, h, w), dtype=torch.float32, device=dev)
+        self.x1, self.x1s = self.l1.alloc_out(), self.l1.alloc_sum()
+        self.x2, self.x3, self.x4 = self.l2.alloc_out(), self.l3.alloc_out(), self.l4.alloc_out()
+        self.x5, self.x5s = self.l5.alloc_out(), self.l5.alloc_sum()
+        self.logits = self.l6.alloc_out()  # [b, h, w, K] channels last
+
+    def flops(self) -> int:
+        return sum(l.flops() for l in self.layers)
+
+    def run_from_input(self) -> torch.Tensor:
+        self.l1.run(self.xin, self.x1, out_sum=self.x1s)
+        self.l2.run(self.x1, self.x2)
+        self.l3.run(self.x2, self.x3)
+        self.l4.run(self.x3, self.x4)
+        self.l5.run(self.x4, self.x5, out_sum=self.x5s)
+        self.l6.run(self.x5s, self.logits, x2=self.x1s)
+        return self.logits
+
+    def run_tokens(self, x_t: torch.Tensor, t: int) -> torch.Tensor:
+        """x_t int64 [b*h*w] token ids, scalar diffusion time t (the sampler uses one t for the whole batch)."""
+        check(lib().sd_denoiser_input(ptr(x_t), ptr(self.xin), self.b, self.h, self.w, int(t), stream_ptr()))
+        return self.run_from_input()
+
+    def run(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """General entry: x float [b,1,h,w], t long [b] (per-sample times, as DummyModel.forward allows)."""
+        self.xin[:, 0:1].copy_(x)
+        self.xin[:, 1:2].copy_(t.to(self.xin.dtype).reshape(-1, 1, 1, 1).expand(-1, 1, self.h, self.w))
+        return self.run_from_input()
+
+
+class SamplerPlan:
+    """AbsorbingDiffusion.sample for a fixed batch shard.
+
+    Philox stream: step i draws its uniforms at generator offset ``offset0 + i*(inc_u + inc_e)`` and its
+    exponentials at ``+ inc_u``, exactly what two consecutive torch CUDA calls (rand_like, exponential_) consume for
+    the GLOBAL batch; a shard [token_base, token_base + n) evaluates only its own elements of that stream.
+    """
+
+    def __init__(self, denoiser_plan: DenoiserPlan, mask_id: int, n_global: Optional[int] = None, shard_base: int = 0):
+        self.dp = denoiser_plan
+        self.mask_id = int(mask_id)
+        dp = denoiser_plan
+        self.n_tokens = dp.b * dp.h * dp.w
+        self.n_tokens_global = (n_global if n_global is not None else dp.b) * dp.h * dp.w
+        self.token_base = shard_base * dp.h * dp.w
+        self.x_t = torch.empty(self.n_tokens, dtype=torch.int64, device=dp.device)
+        self.unmasked = torch.empty(self.n_tokens, dtype=torch.uint8, device=dp.device)
+        inc = ctypes.c_uint64()
+        check(lib().sd_philox_offset_increment(self.n_tokens_global, ctypes.byref(inc)))
+        self.inc_u = inc.value
+        check(lib().sd_philox_offset_increment(self.n_tokens_global * dp.K, ctypes.byref(inc)))
+        self.inc_e = inc.value
+        self.kernel_launches_per_step = 8
+
+    def offset_advance(self, sample_steps: int) -> int:
+        return sample_steps * (self.inc_u + self.inc_e)
+
+    def sample(self, temp: float, sample_steps: int, seed: int, offset0: int = 0,
+               x_init: Optional[torch.Tensor] = None, unmasked_init: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x_init / unmasked_init (host or device, [b,1,h,w] or flat): start from a partially unmasked grid
+        instead of the all-mask grid of vq_diffusion.py:106-107; copied on the current stream (pinned host -> device)."""
+        dp = self.dp
+        L = lib()
+        if x_init is None:
+            self.x_t.fill_(self.mask_id)
+        else:
+            self.x_t.copy_(x_init.reshape(-1), non_blocking=True)
+        if unmasked_init is None:
+            self.unmasked.zero_()
+        else:
+            self.unmasked.copy_(unmasked_init.reshape(-1), non_blocking=True)
+        off = int(offset0)
+        for t in range(sample_steps, 0, -1):
+            logits = dp.run_tokens(self.x_t, t)
+            check(L.sd_sample_step(ptr(logits), ptr(self.x_t), ptr(self.unmasked), None, self.n_tokens, dp.K, t,
+                                   float(temp), int(seed), off, off + self.inc_u, self.token_base,
+                                   self.n_tokens_global, stream_ptr()))
+            off += self.inc_u + self.inc_e
+        return self.x_t.view(dp.b, 1, dp.h, dp.w)
+
+
+# --------------------------------------------------------------------------------------------------
+class VQVAEPlan:
+    """Encoder -> quantiser -> spike generator -> decoder of SNN_VQVAE for a fixed (T, B, H, W)."""
+
+    def __init__(self, model, T: int, B: int, H: int, W: int, nsplit: int = 2):
+        enc, dec, vq = model.encoder.snn_convs, model.decoder.snn_convs, model.vq_layer
+        dev = enc[0].weight.device
+        _require_cuda(enc[0].weight, "SNN_VQVAE parameters")
+        self.T, self.B, self.H, self.W, self.device = T, B, H, W, dev
+        self.D, self.K = vq.embedding_dim, vq.num_embeddings
+        self.in_dim = enc[0].in_channels
+        mk = lambda conv, bn, lif, Hi, Wi, **kw: FusedLayer(conv, bn, lif, T=T, B=B, H_in=Hi, W_in=Wi, nsplit=nsplit, **kw)
+        self.e1 = mk(enc[0], enc[1], enc[2], H, W, in_kind=_lib.IN_REAL_SEQ, out_kind=_lib.OUT_LIF, impl="simt")
+        self.e1c = mk(enc[0], enc[1], enc[2], H, W, in_kind=_lib.IN_REAL_CONST, out_kind=_lib.OUT_LIF, impl="simt")
+        self.e2 = mk(enc[3], enc[4], enc[5], self.e1.H_out, self.e1.W_out, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF)
+        self.e3 = mk(enc[6], enc[7], enc[8], self.e2.H_out, self.e2.W_out, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF)
+        self.h, self.w = self.e3.H_out, self.e3.W_out
+        self.gen = mk(vq.poisson[0], vq.poisson[1], vq.poisson[2], self.h, self.w, in_kind=_lib.IN_REAL_CONST,
+                      out_kind=_lib.OUT_LIF, impl="simt")
+        self.d1 = mk(dec[0], dec[1], dec[2], self.h, self.w, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF)
+        self.d2 = mk(dec[3], dec[4], dec[5], self.d1.H_out, self.d1.W_out, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF)
+        self.d3 = mk(dec[6], None, None, self.d2.H_out, self.d2.W_out, in_kind=_lib.IN_STF,
+                     out_kind=_lib.OUT_MEMOUT_TANH, memout_coef=model.memout.coef)
+        self.s1, self.s2, self.s3 = self.e1.alloc_out(), self.e2.alloc_out(), self.e3.alloc_out()
+        self.z = torch.empty((B * self.h * self.w, self.D), dtype=torch.float32, device=dev)
+        self.idx = torch.empty(B * self.h * self.w, dtype=torch.int64, device=dev)
+        self.margin = torch.empty(B * self.h * self.w, dtype=torch.float32, device=dev)
+        self.q = torch.empty((B, self.D, self.h, self.w), dtype=torch.float32, device=dev)
+        self.sg, self.sd1, self.sd2 = self.gen.alloc_out(), self.d1.alloc_out(), self.d2.alloc_out()
+        self.recon = self.d3.alloc_out()
+        self._vq = vq
+        self._coef_vq = (ctypes.c_float * T)(*vq.memout.coef.detach().reshape(-1).cpu().tolist()[:T])
+
+    def encode(self, x: torch.Tensor, const_over_T: bool = False) -> torch.Tensor:
+        """x: fp32 [T,B,C,H,W] (or [B,C,H,W] with const_over_T=True: the frame repeated T times, R/main.py:133)."""
+        if const_over_T:
+            self.e1c.run(x.contiguous(), self.s1)
+        else:
+            self.e1.run(x.contiguous(), self.s1)
+        self.e2.run(self.s1, self.s2)
+        self.e3.run(self.s2, self.s3)
+        return self.s3
+
+    def quantize_indices(self, spikes_stf: torch.Tensor) -> torch.Tensor:
+        L, vq = lib(), self._vq
+        check(L.sd_vq_feature(ptr(spikes_stf), ptr(vq.alpha.detach()), ctypes.cast(self._coef_vq, ctypes.c_void_p),
+                              ptr(self.z), self.T, self.B, self.D, self.h, self.w, stream_ptr()))
+        check(L.sd_vq_lookup(ptr(self.z), ptr(vq.embeddings.weight.detach()), ptr(self.idx), ptr(self.margin),
+                             self.z.shape[0], self.D, self.K, stream_ptr()))
+        return self.idx
+
+    def generate(self, idx: torch.Tensor) -> torch.Tensor:
+        """code indices [B*h*w] -> generator spikes (STF): quantize -> NCHW -> poisson (vae_model.py:50-57)."""
+        L, vq = lib(), self._vq
+        check(L.sd_vq_gather(ptr(idx), ptr(vq.embeddings.weight.detach()), ptr(self.q), self.B, self.D, self.h, self.w,
+                             self.K, stream_ptr()))
+        self.gen.run(self.q, self.sg)
+        return self.sg
+
+    def decode(self, e_stf: torch.Tensor) -> torch.Tensor:
+        self.d1.run(e_stf, self.sd1)
+        self.d2.run(self.sd1, self.sd2)
+        self.d3.run(self.sd2, self.recon)
+        return self.recon
+
+    def decode_indices(self, idx: torch.Tensor) -> torch.Tensor:
+        """R/main.py:388-399: sampled indices -> tanh(memout(decoder(poisson(quantize(idx)))))."""
+        return self.decode(self.generate(idx.reshape(-1)))
+
+    def forward(self, x: torch.Tensor, const_over_T: bool = False):
+        z = self.encode(x, const_over_T)
+        idx = self.quantize_indices(z)
+        e = self.generate(idx)
+        rec = self.decode(e)
+        return e, rec, idx
+
+    def flops(self) -> int:
+        return sum(l.flops() for l in (self.e1, self.e2, self.e3, self.gen, self.d1, self.d2, self.d3))
+
+
+def to_uint8(pred: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(pred.shape, dtype=torch.uint8, device=pred.device)
+    check(lib().sd_to_uint8(ptr(pred.contiguous()), ptr(out), pred.numel(), stream_ptr()))
+    return out

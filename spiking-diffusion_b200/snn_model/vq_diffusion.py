@@ -1,0 +1,136 @@
+"""Absorbing-state discrete diffusion and its spiking conv denoiser (mirrors R/snn_model/vq_diffusion.py:43-208).
+
+Same class names, constructor arguments, attributes (``n_samples``, ``num_timesteps``, ``shape``, ``mask_id``,
+``num_embeddings``) and ``state_dict`` keys (``conv{1..5}.{0,1}.*``, ``conv6.0.*``).  Additive differences:
+* ``DummyModel(..., T=16)``: the reference hard-codes 16 timesteps (vq_diffusion.py:198,206);
+* ``AbsorbingDiffusion(..., shape=(7,7), n_samples=16)``: the reference hard-codes the 7x7 grid, 49 steps and 16
+  samples (vq_diffusion.py:47-51); they remain plain attributes that callers may overwrite, as in the reference;
+* ``sample(..., seed=None)``: with ``seed=None`` the sampler consumes torch's CUDA generator exactly as the
+  reference's two draws per step would (seed and offset are read from, and advanced on, the default generator),
+  so ``torch.manual_seed(s); sample()`` reproduces the reference's stream.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib, engine
+from .._lib import check, lib, ptr, stream_ptr
+from ..activation_based import functional, layer, neuron, surrogate
+
+
+class DummyModel(nn.Module):
+    """6-layer spiking conv denoiser with one skip connection (vq_diffusion.py:150-208)."""
+
+    def __init__(self, n_channel: int, num_embeddings, T: int = 16) -> None:
+        super().__init__()
+        self.num_embeddings = num_embeddings
+        self.T = T
+        def block(cin, cout):
+            return layer.SpikingSequential(
+                layer.Conv2d(in_channels=cin, out_channels=cout, kernel_size=3, stride=1, padding=1),
+                layer.BatchNorm2d(cout),
+                neuron.LIFNode(surrogate_function=surrogate.ATan()))
+        self.conv1 = block(n_channel * 2, 64)
+        self.conv2 = block(64, 128)
+        self.conv3 = block(128, 256)
+        self.conv4 = block(256, 512)
+        self.conv5 = block(512, 256)
+        self.conv6 = layer.SpikingSequential(layer.Conv2d(256 + 64, num_embeddings, 3, 1, 1))
+        self._plans = {}
+        self.nsplit = 2   # fp16 terms per fp32 weight in the tcgen05 layers (2 = 22-bit weights, 1 = 11-bit)
+
+    def plan(self, b: int, h: int, w: int) -> "engine.DenoiserPlan":
+        key = (self.T, b, h, w, self.nsplit, tuple(p._version for p in self.parameters()),
+               tuple(bf._version for bf in self.buffers()), next(self.parameters()).device)
+        if self._plans.get("key") != key:
+            self._plans = {"key": key, "plan": engine.DenoiserPlan(self, self.T, b, h, w, nsplit=self.nsplit)}
+        return self._plans["plan"]
+
+    def forward(self, x, t) -> torch.Tensor:
+        """x: [b, 1, h, w] float token ids, t: [b] long -> logits [b, K, h, w]  (vq_diffusion.py:189-208).
+
+        The whole network runs as one fused chain, so the per-layer LIF states are consumed inside the kernels:
+        this equals the reference whenever the net is reset between calls, which every reference call site does
+        (vq_diffusion.py:129, R/main.py:249,391)."""
+        if self.training:
+            raise NotImplementedError("training mode is not implemented in this round (SURVEY.md section 8(f) rank 1)")
+        if not x.is_cuda:
+            raise RuntimeError("DummyModel.forward needs CUDA tensors: there is no CPU path")
+        for m in self.modules():
+            if isinstance(m, neuron.LIFNode) and isinstance(m.v, torch.Tensor):
+                raise RuntimeError("DummyModel.forward starts from reset LIF state; call functional.reset_net(model) first")
+        b, _, h, w = x.shape
+        logits = self.plan(b, h, w).run(x.float(), t)
+        return logits.permute(0, 3, 1, 2).contiguous()
+
+
+class Sampler(nn.Module):
+    def __init__(self):
+        super().__init__()
+
+
+class AbsorbingDiffusion(Sampler):
+    def __init__(self, denoise_fn, mask_id, shape=(7, 7), n_samples: int = 16):
+        super().__init__()
+        self.num_classes = denoise_fn.num_embeddings
+        self.shape = list(shape)
+        self.num_timesteps = int(shape[0] * shape[1])
+        self.mask_id = mask_id
+        self._denoise_fn = denoise_fn
+        self.n_samples = n_samples
+        self.mask_schedule = "random"
+        self.loss_type = "reweighted_elbo"
+        self._plans = {}
+
+    def sample_time(self, b, device):
+        t = torch.randint(1, self.num_timesteps + 1, (b,), device=device).long()
+        pt = torch.ones_like(t).float() / self.num_timesteps
+        return t, pt
+
+    def q_sample(self, x_0, t):
+        """Forward (masking) process (vq_diffusion.py:61-72); plain tensor algebra, training path only."""
+        x_t, x_0_ignore = x_0.clone(), x_0.clone()
+        t_mask = t.reshape(x_0.shape[0], 1, 1, 1).expand(x_0.shape[0], 1, *self.shape)
+        mask = torch.rand_like(x_t.float()) < (t_mask.float() / self.num_timesteps)
+        x_t[mask] = self.mask_id
+        x_0_ignore[torch.bitwise_not(mask)] = -1
+        return x_t, x_0_ignore, mask
+
+    def _train_loss(self, x_0):
+        raise NotImplementedError("the diffusion training loss needs the denoiser backward pass "
+                                  "(SURVEY.md section 8(f) rank 1, not in this round)")
+
+    def train_iter(self, x):
+        return {"loss": self._train_loss(x)}
+
+    def plan(self, b: int, n_global=None, shard_base: int = 0) -> "engine.SamplerPlan":
+        h, w = self.shape
+        dp = self._denoise_fn.plan(b, h, w)
+        key = (id(dp), int(self.mask_id), n_global, shard_base)
+        if self._plans.get("key") != key:
+            self._plans = {"key": key, "plan": engine.SamplerPlan(dp, int(self.mask_id), n_global, shard_base)}
+        return self._plans["plan"]
+
+    @torch.no_grad()
+    def sample(self, temp=1.0, sample_steps=None, seed=None, offset=0, n_global=None, shard_base: int = 0,
+               x_init=None, unmasked_init=None):
+        """Reverse process (vq_diffusion.py:103-142) -> x_t int64 [b, 1, h, w] with no mask tokens left.
+
+        ``n_global`` / ``shard_base``: this call generates images [shard_base, shard_base + n_samples) of a global
+        batch of ``n_global``; each shard evaluates the Philox values of its global element indices, so sharding the
+        batch over GPUs reproduces the single-GPU stream (no collective on this path)."""
+        if self._denoise_fn.training:
+            raise NotImplementedError("sample() runs the denoiser in eval mode; call denoise_fn.eval()")
+        b = int(self.n_samples)
+        if sample_steps is None:
+            raise TypeError("unsupported operand type(s) for +: 'NoneType' and 'int'")  # the reference's failure mode
+        plan = self.plan(b, n_global, shard_base)
+        if seed is None:
+            gen = torch.cuda.default_generators[torch.cuda.current_device()]
+            seed, offset = gen.initial_seed(), gen.get_offset()
+            gen.set_offset(offset + plan.offset_advance(sample_steps))
+        x_t = plan.sample(float(temp), int(sample_steps), int(seed), int(offset), x_init, unmasked_init)
+        functional.reset_net(self._denoise_fn)
+        return x_t.clone()

@@ -1,0 +1,13 @@
+"""Import alias: the package directory is ``spiking-diffusion_b200`` (hyphenated, as the repo layout requires),
+which is not a valid Python identifier.  ``import spiking_diffusion_b200`` executes this file, which loads that
+directory as the package ``spiking_diffusion_b200`` and replaces itself in ``sys.modules``."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "spiking-diffusion_b200")
+_spec = importlib.util.spec_from_file_location(__name__, os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

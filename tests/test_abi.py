@@ -1,0 +1,86 @@
+"""The C-ABI library loads on a CPU-only box, exports exactly what include/sd_b200.h declares, and refuses to
+compute without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+import spiking_diffusion_b200 as sd
+from spiking_diffusion_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "sd_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sd_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert header_symbols() == sorted(_lib.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    for name in header_symbols():
+        assert hasattr(L, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (sd_[a-z0-9_]+)$", out, flags=re.M))
+    assert exported == set(header_symbols())
+
+
+def test_struct_layout_matches_header():
+    # 17 ints + 3 floats + 2 ints, no padding; 9 pointers
+    assert ctypes.sizeof(_lib.ConvDesc) == 22 * 4
+    assert ctypes.sizeof(_lib.ConvArgs) == 9 * ctypes.sizeof(ctypes.c_void_p)
+
+
+def test_geometry_queries_are_host_only():
+    L = _lib.lib()
+    assert L.sd_version() == 1
+    assert L.sd_stf_guard(7) == 16 and L.sd_stf_guard(28) == 32
+    # 256 images of an 8x8 padded grid = 16384 rows = 128 tiles of 128, + 2 guards
+    assert L.sd_stf_rows(256, 7, 7) == 16384 + 32
+    assert L.sd_stf_bytes(4, 256, 64, 7, 7) == 4 * 8 * (16384 + 32) * 8 * 2
+    assert L.sd_stf_bytes(1, 1, 3, 7, 7) == 1 * 1 * (128 + 32) * 8 * 2  # C rounded up to 8
+
+
+def test_argument_errors_mirror_reference_exceptions():
+    L = _lib.lib()
+    # LIFNode asserts tau > 1 (SJ/activation_based/neuron.py:707) -> SD_ERR_INVALID -> ValueError
+    rc = L.sd_lif_forward(None, None, None, None, 4, 16, 1.0, 1.0, 0.0, 1, 1, None)
+    assert rc == _lib.SD_ERR_INVALID
+    with pytest.raises(ValueError):
+        _lib.check(rc)
+    assert b"tau" in L.sd_last_error()
+    # empty input is a no-op, like the reference on an empty tensor
+    assert L.sd_lif_forward(None, None, None, None, 0, 0, 2.0, 1.0, 0.0, 1, 1, None) == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    L = _lib.lib()
+    x = torch.zeros(4, 16)
+    rc = L.sd_lif_forward(x.data_ptr(), x[0].data_ptr(), x.data_ptr(), None, 4, 16, 2.0, 1.0, 0.0, 1, 1, None)
+    assert rc == _lib.SD_ERR_NO_DEVICE
+    with pytest.raises(sd.SdError):
+        _lib.check(rc)
+    from spiking_diffusion_b200.activation_based import neuron
+    n = neuron.LIFNode(step_mode="m").eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        n(torch.zeros(4, 8))
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under the package may import or execute it."""
+    pkg = os.path.join(ROOT, "spiking-diffusion_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "snn_oracle" not in text, f

@@ -1,0 +1,122 @@
+"""Host-side logic that needs no GPU: module structure / state_dict compatibility with the reference, the
+step-mode and memory protocol, BN folding arithmetic, shard bookkeeping."""
+import os
+
+import pytest
+import torch
+
+from oracle import snn_oracle as O
+from spiking_diffusion_b200 import engine, synth
+from spiking_diffusion_b200.activation_based import base, functional, layer, neuron, surrogate
+from spiking_diffusion_b200.snn_model.vae_model import SNN_VQVAE, VectorQuantizer
+from spiking_diffusion_b200.snn_model.vq_diffusion import AbsorbingDiffusion, DummyModel
+
+REF_VQVAE_KEYS = (
+    [f"encoder.snn_convs.{i}.{k}" for i in (0, 3, 6) for k in ("weight", "bias")]
+    + [f"encoder.snn_convs.{i}.{k}" for i in (1, 4, 7)
+       for k in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")]
+    + ["vq_layer.alpha", "vq_layer.memout.coef", "vq_layer.embeddings.weight"]
+    + [f"vq_layer.poisson.0.{k}" for k in ("weight", "bias")]
+    + [f"vq_layer.poisson.1.{k}" for k in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")]
+    + [f"decoder.snn_convs.{i}.{k}" for i in (0, 3, 6) for k in ("weight", "bias")]
+    + [f"decoder.snn_convs.{i}.{k}" for i in (1, 4)
+       for k in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")]
+    + ["memout.coef"])
+
+
+def test_state_dict_keys_match_reference_checkpoint_format():
+    """Key list of SURVEY.md section 8(f) rank 3 (R/main.py:199,286 checkpoints)."""
+    m = SNN_VQVAE(1, 16, 128, torch.tensor(1.0))
+    assert sorted(m.state_dict().keys()) == sorted(REF_VQVAE_KEYS)
+    assert m.state_dict()["memout.coef"].shape == (16, 1, 1, 1, 1)          # default T = 16, as the reference
+    d = DummyModel(1, 128)
+    keys = sorted(d.state_dict().keys())
+    want = sorted([f"conv{i}.0.{k}" for i in range(1, 7) for k in ("weight", "bias")]
+                  + [f"conv{i}.1.{k}" for i in range(1, 6)
+                     for k in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")])
+    assert keys == want
+    assert sum(p.numel() for p in d.parameters()) == 3101504
+    assert sum(p.numel() for p in m.parameters()) == 50658
+    # LIF state is not part of the state dict (SJ/activation_based/base.py:170-171)
+    assert not any(k.endswith(".v") for k in keys)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference not mounted")
+def test_reference_state_dicts_load_into_our_modules_and_back():
+    from oracle import ref_loader
+    R = ref_loader.load()
+    ours, theirs = SNN_VQVAE(1, 16, 128, torch.tensor(1.0)), R.SNN_VQVAE(1, 16, 128, torch.tensor(1.0))
+    assert ours.load_state_dict(theirs.state_dict()).missing_keys == []
+    assert theirs.load_state_dict(ours.state_dict()).missing_keys == []
+    od, td = DummyModel(1, 128), R.DummyModel(1, 128)
+    od.load_state_dict(td.state_dict()); td.load_state_dict(od.state_dict())
+
+
+def test_step_mode_and_memory_protocol():
+    n = neuron.LIFNode(surrogate_function=surrogate.ATan())
+    assert n.step_mode == "s" and n.backend == "torch" and n.v == 0.0 and n.tau == 2.0 and n.v_threshold == 1.0
+    m = SNN_VQVAE(1, 16, 128, torch.tensor(1.0))
+    functional.set_step_mode(m, "m")
+    assert all(x.step_mode == "m" for x in m.modules() if hasattr(x, "step_mode"))
+    functional.set_backend(m, "cupy")      # accepted name; same kernel, no dispatch
+    n.v = torch.ones(3)
+    assert "v" not in n.state_dict() and list(dict(n.named_memories())) == ["v"]
+    n.reset()
+    assert n.v == 0.0
+    soft = neuron.LIFNode(v_reset=None)
+    assert soft.v == 0.0 and soft.v_reset is None
+    with pytest.raises(ValueError):
+        n.step_mode = "q"
+    with pytest.raises(NotImplementedError):
+        n.backend = "lava"
+    with pytest.raises(AssertionError):
+        neuron.LIFNode(tau=2)               # isinstance(tau, float), neuron.py:707
+    rep = n._replicate_for_data_parallel()
+    assert rep._memories is not n._memories and rep.v == n.v
+
+
+def test_sequential_grouping():
+    d = DummyModel(1, 128)
+    st = d.conv1._stages()
+    assert len(st) == 1 and isinstance(st[0][2], neuron.LIFNode)
+    assert d.conv6._stages()[0][1] is None and d.conv6._stages()[0][2] is None
+    enc = SNN_VQVAE(1, 16, 128, 1.0).encoder.snn_convs
+    assert [type(s[0]).__name__ for s in enc._stages()] == ["Conv2d"] * 3
+
+
+def test_bn_fold_matches_conv_then_bn():
+    g = torch.Generator().manual_seed(0)
+    conv = torch.nn.Conv2d(5, 7, 3, padding=1)
+    bn = torch.nn.BatchNorm2d(7).eval()
+    with torch.no_grad():
+        bn.running_mean.copy_(torch.rand(7, generator=g)); bn.running_var.copy_(torch.rand(7, generator=g) + 0.2)
+        bn.weight.copy_(torch.rand(7, generator=g) + 0.5); bn.bias.copy_(torch.rand(7, generator=g))
+    x = torch.randn(2, 5, 6, 6, generator=g)
+    scale, shift = engine.fold_bn(conv.bias, 7, bn, "cpu")
+    y = torch.nn.functional.conv2d(x, conv.weight, None, padding=1) * scale[None, :, None, None] + shift[None, :, None, None]
+    assert float((y - bn(conv(x))).abs().max()) <= 1e-5
+    p = {"c.bias": conv.bias.detach(), "b.weight": bn.weight.detach(), "b.bias": bn.bias.detach(),
+         "b.running_mean": bn.running_mean, "b.running_var": bn.running_var}
+    s2, h2 = O.bn_affine(p, "c", "b")
+    assert torch.allclose(s2, scale) and torch.allclose(h2, shift)
+
+
+def test_cpu_tensors_are_rejected_not_silently_computed():
+    m = SNN_VQVAE(1, 16, 128, torch.tensor(1.0), T=4).eval()
+    functional.set_step_mode(m, "m")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(4, 1, 1, 28, 28), torch.zeros(1, 1, 28, 28))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        DummyModel(1, 128, T=4).eval()(torch.zeros(1, 1, 7, 7), torch.ones(1).long())
+    with pytest.raises(NotImplementedError):
+        SNN_VQVAE(1, 16, 128, 1.0)(torch.zeros(16, 1, 1, 28, 28), None)      # train mode: not this round
+
+
+def test_absorbing_diffusion_attributes():
+    ab = AbsorbingDiffusion(DummyModel(1, 128, T=4), mask_id=128)
+    assert (ab.n_samples, ab.num_timesteps, ab.shape, ab.mask_id, ab.num_classes) == (16, 49, [7, 7], 128, 128)
+    ab8 = AbsorbingDiffusion(DummyModel(3, 128, T=4), mask_id=128, shape=(8, 8), n_samples=1024)
+    assert ab8.num_timesteps == 64
+    x0 = torch.randint(0, 128, (4, 1, 7, 7))
+    x_t, ign, mask = ab.q_sample(x0, torch.tensor([49, 1, 25, 49]))
+    assert bool((x_t[mask] == 128).all()) and bool((ign[~mask] == -1).all())
