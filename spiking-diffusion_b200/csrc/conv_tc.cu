@@ -132,6 +132,20 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
          ((uint64_t)1 << 46);
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+
 struct PipeState {
   int stage = 0;
   uint32_t phase = 0;
@@ -143,6 +157,9 @@ struct PipeState {
 // ---------------------------------------------------------------------------------------------------
 // Kernel
 // ---------------------------------------------------------------------------------------------------
+// NSPLIT = fp16 terms per weight, KSTEPS = KBLK / 16 (tcgen05.mma K = 16): compile-time so that the MMA issue loop
+// unrolls into descriptor-low-word additions with immediates.
+template <int NSPLIT, int KSTEPS>
 __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcConfig& c = p.c;
@@ -206,62 +223,75 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
       }
     }
   } else if (warp == 9) {
-    // ===== B producer =====
-    if (lane == 0) {
-      PipeState st;
-      const int64_t stage_halfs = c.b_stage_bytes / 2;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % c.n_tiles;
-        const __half* wsrc = p.wpack + (int64_t)n_tile * c.num_kblocks * 9 * stage_halfs;
-        for (int it = 0; it < c.num_kblocks * 9; ++it) {
-          mbar_wait(b_empty(st.stage), st.phase ^ 1);
+    // ===== B producer (whole warp converged; one elected lane issues) =====
+    PipeState st;
+    const int64_t stage_halfs = c.b_stage_bytes / 2;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % c.n_tiles;
+      const __half* wsrc = p.wpack + (int64_t)n_tile * c.num_kblocks * 9 * stage_halfs;
+      for (int it = 0; it < c.num_kblocks * 9; ++it) {
+        mbar_wait(b_empty(st.stage), st.phase ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(b_full(st.stage), c.b_stage_bytes);
           bulk_g2s(b_base + st.stage * c.b_stage_bytes, wsrc + (int64_t)it * stage_halfs, c.b_stage_bytes,
                    b_full(st.stage));
-          st.advance(c.b_stages);
         }
+        __syncwarp();
+        st.advance(c.b_stages);
       }
     }
   } else if (warp == 10) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      PipeState sa, sb, sc;
-      const uint32_t b_split_bytes = (uint32_t)chunks * c.N_TILE * 16u;
-      const uint32_t b_lbo = (uint32_t)c.N_TILE * 16u;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(acc_empty(sc.stage), sc.phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_base = tmem_base + (uint32_t)(sc.stage * c.T_acc * c.N_TILE);
-        for (int kb = 0; kb < c.num_kblocks; ++kb) {
-          mbar_wait(a_full(sa.stage), sa.phase);
+    // ===== MMA issuer (whole warp converged; one elected lane issues tcgen05.mma / tcgen05.commit) =====
+    PipeState sa, sb, sc;
+    // descriptor words: lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version(1)<<14; all stepping is done on lo
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lo_const = (plane_bytes >> 4) << 16;
+    const uint32_t b_lbo = (uint32_t)c.N_TILE * 16u;
+    const uint32_t b_lo_const = (b_lbo >> 4) << 16;
+    const uint32_t a_step_t = ((uint32_t)chunks * plane_bytes) >> 4;
+    const uint32_t a_step_k = (2u * plane_bytes) >> 4;
+    const uint32_t b_step_sp = ((uint32_t)chunks * b_lbo) >> 4;
+    const uint32_t b_step_k = (2u * b_lbo) >> 4;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(acc_empty(sc.stage), sc.phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + (uint32_t)(sc.stage * c.T_acc * c.N_TILE);
+      for (int kb = 0; kb < c.num_kblocks; ++kb) {
+        mbar_wait(a_full(sa.stage), sa.phase);
+        const uint32_t a_stage = a_base + sa.stage * c.a_stage_bytes;
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(b_full(sb.stage), sb.phase);
           tc_fence_after();
-          const uint32_t a_stage = a_base + sa.stage * c.a_stage_bytes;
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(b_full(sb.stage), sb.phase);
-            tc_fence_after();
-            const uint32_t b_stage = b_base + sb.stage * c.b_stage_bytes;
+          if (elect_one()) {
             const int shift = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
-            const uint32_t a_row_off = (uint32_t)(c.halo + shift) * 16u;
+            uint32_t a_lo = a_lo_const | ((a_stage + (uint32_t)(c.halo + shift) * 16u) >> 4);
+            const uint32_t b_lo0 = b_lo_const | ((b_base + sb.stage * c.b_stage_bytes) >> 4);
+            uint32_t d = d_base;
+            const uint32_t first = (kb | tap) != 0 ? 1u : 0u;
             for (int t = 0; t < c.T_acc; ++t) {
-              for (int sp = 0; sp < p.nsplit; ++sp) {
-                for (int ks = 0; ks < (c.KBLK >> 4); ++ks) {
-                  const uint64_t adesc =
-                      make_desc(a_stage + (uint32_t)(t * chunks + 2 * ks) * plane_bytes + a_row_off, plane_bytes, 128);
-                  const uint64_t bdesc = make_desc(b_stage + sp * b_split_bytes + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128);
-                  const uint32_t accum = (kb | tap | sp | ks) != 0 ? 1u : 0u;
-                  tc_mma_f16(d_base + (uint32_t)(t * c.N_TILE), adesc, bdesc, p.idesc, accum);
+#pragma unroll
+              for (int sp = 0; sp < NSPLIT; ++sp) {
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                  const uint64_t adesc = ((uint64_t)desc_hi << 32) | (a_lo + ks * a_step_k);
+                  const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (b_lo0 + sp * b_step_sp + ks * b_step_k);
+                  tc_mma_f16(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first);
                 }
               }
+              a_lo += a_step_t;
+              d += (uint32_t)c.N_TILE;
             }
             tc_commit(b_empty(sb.stage));
-            sb.advance(c.b_stages);
+            if (tap == 8) tc_commit(a_empty(sa.stage));
           }
-          tc_commit(a_empty(sa.stage));
-          sa.advance(c.a_stages);
+          __syncwarp();
+          sb.advance(c.b_stages);
         }
-        tc_commit(acc_full(sc.stage));
-        sc.advance(c.acc_stages);
+        sa.advance(c.a_stages);
       }
+      if (elect_one()) tc_commit(acc_full(sc.stage));
+      __syncwarp();
+      sc.advance(c.acc_stages);
     }
   } else if (warp < 8) {
     // ===== epilogue =====
@@ -270,6 +300,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     const int col_lo = (warp >> 2) * (c.N_TILE >> 1);
     const int col_hi = col_lo + (c.N_TILE >> 1);
     const float inv_T = 1.0f / (float)p.T;
+    // x / tau == x * (1/tau) bit for bit when tau is a power of two (the reference uses tau = 2)
+    int tau_exp;
+    const bool tau_pow2 = frexpf(p.tau, &tau_exp) == 0.5f;
+    const float inv_tau = 1.0f / p.tau;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n0 = (tile % c.n_tiles) * c.N_TILE;
       const int64_t r = (int64_t)(tile / c.n_tiles) * kTileRows + q * 32 + lane;  // padded row (without guard)
@@ -315,9 +349,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float x = fmaf(__uint_as_float(acc[j]), sc_[j], sh_[j]);
-              float h;
-              if (p.hard_reset) h = __fadd_rn(v[j], __fdiv_rn(__fsub_rn(x, __fsub_rn(v[j], p.v_reset)), p.tau));
-              else              h = __fadd_rn(v[j], __fdiv_rn(__fsub_rn(x, v[j]), p.tau));
+              const float dv = p.hard_reset ? __fsub_rn(x, __fsub_rn(v[j], p.v_reset)) : __fsub_rn(x, v[j]);
+              const float h = __fadd_rn(v[j], tau_pow2 ? __fmul_rn(dv, inv_tau) : __fdiv_rn(dv, p.tau));
               const bool s = h >= p.v_th;
               v[j] = p.hard_reset ? (s ? p.v_reset : h) : (s ? __fsub_rn(h, p.v_th) : h);
               cnt[j] += s ? 1.f : 0.f;
@@ -580,14 +613,26 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
   // cute::UMMA::InstrDescriptor: c_format F32 (bit 4), a/b F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
   p.idesc = (1u << 4) | ((uint32_t)(c.N_TILE >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
   p.c = c;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SD_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   int grid = c.m_tiles * c.n_tiles;
   if (grid > sm_count()) grid = sm_count();
-  conv3x3_tc_kernel<<<grid, kTcThreads, c.smem_bytes, as_stream(stream)>>>(p);
+  cudaStream_t st = as_stream(stream);
+#define SD_TC_LAUNCH(NS, KS)                                                                                       \
+  do {                                                                                                             \
+    static bool attr_set = false;                                                                                  \
+    if (!attr_set) {                                                                                               \
+      SD_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<NS, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                   227 * 1024));                                                                   \
+      attr_set = true;                                                                                             \
+    }                                                                                                              \
+    conv3x3_tc_kernel<NS, KS><<<grid, kTcThreads, c.smem_bytes, st>>>(p);                                          \
+  } while (0)
+  const int ks = c.KBLK / 16;
+  if (d->nsplit == 1) {
+    if (ks == 1) SD_TC_LAUNCH(1, 1); else if (ks == 2) SD_TC_LAUNCH(1, 2); else SD_TC_LAUNCH(1, 4);
+  } else {
+    if (ks == 1) SD_TC_LAUNCH(2, 1); else if (ks == 2) SD_TC_LAUNCH(2, 2); else SD_TC_LAUNCH(2, 4);
+  }
+#undef SD_TC_LAUNCH
   SD_LAUNCH_CHECK();
   return SD_OK;
 }

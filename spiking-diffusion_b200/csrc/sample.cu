@@ -64,11 +64,13 @@ __device__ __forceinline__ float torch_uniform(uint32_t raw) {
   float v = u32_to_uniform(raw);
   return v == 1.0f ? 0.0f : v;
 }
-// Tensor.exponential_(1): -log(u) with the u >= 1 - eps/2 guard        (TransformationHelper.h:129-146)
+// Tensor.exponential_(1): -log(u) with the u >= 1 - eps/2 guard        (TransformationHelper.h:129-146).
+// at::log<float> on the device is the fast __logf approximation (TORCH/include/ATen/NumericUtils.h:150-157), so
+// the same intrinsic is used here: measured bit-identical to torch on the B200 (tests/test_gpu_sampling.py).
 __device__ __forceinline__ float torch_exponential(uint32_t raw) {
   float v = u32_to_uniform(raw);
   const float eps = 1.1920928955078125e-07f;
-  float lg = (v >= 1.0f - eps / 2.0f) ? (-eps / 2.0f) : logf(v);
+  float lg = (v >= 1.0f - eps / 2.0f) ? (-eps / 2.0f) : __logf(v);
   return __fmul_rn(-1.0f, lg);  // (-1 / lambda) * log with lambda = 1
 }
 

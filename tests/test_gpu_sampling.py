@@ -52,10 +52,11 @@ def test_uniform_and_exponential_match_torch_cuda(numel):
     assert inc_u == off1 and inc_e == off2 - off1           # generator bookkeeping identical to torch's
     assert torch.equal(u, ref_u)
     assert torch.equal(e, ref_e)
-    # the numpy oracle is pinned by the same comparison (uniform exact; exponential up to libm's last bit)
+    # the numpy oracle is pinned by the same comparison: uniform exact; exponential to the accuracy of the device's
+    # __logf (abs 2^-21.4 on [0.5, 2], 3 ulp elsewhere), which numpy's correctly rounded log cannot reproduce bitwise
     assert np.array_equal(philox.uniform(1234, 0, numel, sms, thr), ref_u.cpu().numpy())
     eo = philox.exponential(1234, off1, numel, sms, thr)
-    assert np.allclose(eo, ref_e.cpu().numpy(), rtol=3e-7, atol=0)
+    assert np.allclose(eo, ref_e.cpu().numpy(), rtol=1e-6, atol=1e-6)
     # a shard of the stream equals the slice of the whole
     if numel > 1000:
         part, _ = ours("u", numel, 1234, 0, base=777, n=200)
