@@ -165,6 +165,103 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtParams p) {
   }
 }
 
+// Real-valued input that is constant over T (enc.conv1, den.conv1, vq.poisson): the convolution is evaluated once
+// and the LIF runs on a constant current.  One thread = one output pixel x 8 output channels, so every timestep's
+// spikes leave as ONE 16-byte store into the STF plane, consecutive lanes -> consecutive rows (coalesced); the
+// 8-channel weight slice is a warp-uniform 2 x float4 load per (tap, ci) from the packed [tap][ci][co] array.
+template <int TMAX>
+__global__ void __launch_bounds__(256) conv_real_const_lif_kernel(const SimtParams p) {
+  const sd_conv_desc& d = p.d;
+  const int T = d.T, Cout = d.C_out, Cin = d.C_in;
+  const int Cout8 = Cout >> 3;
+  const int64_t npix = (int64_t)d.B * d.H_out * d.W_out;
+  const int64_t total = npix * Cout8;
+  const StfGeom gout(d.B, d.H_out, d.W_out);
+  const float* __restrict__ xin = (const float*)p.in;
+  const int64_t plane = (int64_t)d.H_in * d.W_in;
+  const float inv_tau = 1.0f / d.tau;
+  int tau_exp;
+  const bool fast = frexpf(d.tau, &tau_exp) == 0.5f && d.hard_reset && d.v_reset == 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int chunk = (int)(i / npix);
+    int pix = (int)(i - (int64_t)chunk * npix);
+    const int ox = pix % d.W_out; pix /= d.W_out;
+    const int oy = pix % d.H_out;
+    const int b = pix / d.H_out;
+    const int co = chunk << 3;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int ky = 0; ky < d.kh; ++ky) {
+      const int iy = oy * d.stride - d.pad + ky;
+      if (iy < 0 || iy >= d.H_in) continue;
+      for (int kx = 0; kx < d.kw; ++kx) {
+        const int ix = ox * d.stride - d.pad + kx;
+        if (ix < 0 || ix >= d.W_in) continue;
+        const float* wt = p.w + (int64_t)(ky * d.kw + kx) * Cin * Cout + co;
+        const float* xp = xin + ((int64_t)b * Cin) * plane + (int64_t)iy * d.W_in + ix;
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float xv = xp[(int64_t)ci * plane];
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt + (int64_t)ci * Cout));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + (int64_t)ci * Cout + 4));
+          acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+          acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+          acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+          acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+        }
+      }
+    }
+    const int64_t orow = gout.row(b, oy, ox);
+    const int64_t vidx = ((int64_t)chunk * gout.R_alloc + orow) * 8;
+    float x[8], v[8], cnt[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      x[j] = fmaf(acc[j], p.scale[co + j], p.shift[co + j]);
+      v[j] = p.v ? p.v[vidx + j] : (d.hard_reset ? d.v_reset : 0.f);
+      cnt[j] = 0.f;
+    }
+    __half* outp = (__half*)p.out;
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) {
+      if (t < T) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float h;
+          bool s;
+          if (fast) {
+            h = fmaf(__fsub_rn(x[j], v[j]), inv_tau, v[j]);
+            s = h >= d.v_threshold;
+            v[j] = s ? 0.f : h;
+          } else {
+            const float dv = d.hard_reset ? __fsub_rn(x[j], __fsub_rn(v[j], d.v_reset)) : __fsub_rn(x[j], v[j]);
+            h = __fadd_rn(v[j], __fdiv_rn(dv, d.tau));
+            s = h >= d.v_threshold;
+            v[j] = d.hard_reset ? (s ? d.v_reset : h) : (s ? __fsub_rn(h, d.v_threshold) : h);
+          }
+          cnt[j] += s ? 1.f : 0.f;
+          const uint32_t bits = s ? 0x3C00u : 0u;
+          if (j & 1) pk[j >> 1] |= bits << 16; else pk[j >> 1] = bits;
+        }
+        *reinterpret_cast<uint4*>(outp + gout.at(t, Cout8, co, orow)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+    if (p.v) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p.v[vidx + j] = v[j];
+    }
+    if (p.out_sum) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const __half2 h2 = __floats2half2_rn(cnt[j], cnt[j + 1]);
+        pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      *reinterpret_cast<uint4*>(p.out_sum + gout.at(0, Cout8, co, orow)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
 // w (reference layout) -> [tap][ci][co]
 __global__ void pack_simt_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int kh,
                                  int kw, int transposed) {
@@ -251,6 +348,17 @@ int sd_conv_lif_simt(const sd_conv_desc* d, const sd_conv_args* a, void* stream)
   int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   cudaStream_t st = as_stream(stream);
+  if (d->in_kind == SD_IN_REAL_CONST && d->out_kind == SD_OUT_LIF && !d->transposed && d->C_out % 8 == 0) {
+    int64_t n8 = (int64_t)d->B * d->H_out * d->W_out * (d->C_out / 8);
+    int64_t bl = (n8 + 255) / 256;
+    if (bl > cap) bl = cap;
+    if (d->T <= 4) conv_real_const_lif_kernel<4><<<(unsigned)bl, 256, 0, st>>>(p);
+    else if (d->T <= 8) conv_real_const_lif_kernel<8><<<(unsigned)bl, 256, 0, st>>>(p);
+    else if (d->T <= 16) conv_real_const_lif_kernel<16><<<(unsigned)bl, 256, 0, st>>>(p);
+    else conv_real_const_lif_kernel<32><<<(unsigned)bl, 256, 0, st>>>(p);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+  }
   // TMAX bounds both the accumulator array and the unrolled epilogue; pick the smallest that fits T.
   if (d->T <= 4) conv_simt_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(p);
   else if (d->T <= 8) conv_simt_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(p);

@@ -45,6 +45,9 @@ struct TcConfig {
   int acc_stages;
   int a_stages, b_stages;
   int halo, rows_ld;
+  int ndx;         // 1: one copy of the rows, taps shift by dy*Wp+dx rows (16-byte aligned starts);
+                   // 3: three copies pre-shifted by dx = -1,0,+1 so that every tap start is 128-byte aligned
+                   //    (needs Wp % 8 == 0): shared-memory operand fetch of a misaligned core matrix costs 2x
   uint32_t a_stage_bytes, b_stage_bytes, smem_bytes;
   int n_tiles, m_tiles, num_kblocks, c0_blocks;
 };
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
   if (warp == 8) {
     // ===== A producer =====
     PipeState st;
-    const int ncopy = c.T_acc * chunks;
+    const int ncopy = c.T_acc * chunks * c.ndx;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int64_t row0 = (int64_t)(tile / c.n_tiles) * kTileRows;
       for (int kb = 0; kb < c.num_kblocks; ++kb) {
@@ -215,8 +218,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
         const int C8 = seg1 ? p.C8_1 : p.C8_0;
         const int chunk0 = (seg1 ? kb - c.c0_blocks : kb) * chunks;
         for (int i = lane; i < ncopy; i += 32) {
-          const int t = i / chunks, ch = i - t * chunks;
-          const __half* g = src + ((((int64_t)t * C8 + chunk0 + ch) * p.R_alloc) + p.G + row0 - c.halo) * 8;
+          const int pl = i / c.ndx, dxi = i - pl * c.ndx;          // plane (t, chunk) and its dx copy
+          const int t = pl / chunks, ch = pl - t * chunks;
+          const int dx = c.ndx == 3 ? dxi - 1 : 0;
+          const __half* g = src + ((((int64_t)t * C8 + chunk0 + ch) * p.R_alloc) + p.G + row0 - c.halo + dx) * 8;
           bulk_g2s(a_base + st.stage * c.a_stage_bytes + (uint32_t)i * plane_bytes, g, plane_bytes, a_full(st.stage));
         }
         st.advance(c.a_stages);
@@ -245,11 +250,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     PipeState sa, sb, sc;
     // descriptor words: lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version(1)<<14; all stepping is done on lo
     const uint32_t desc_hi = (128u >> 4) | (1u << 14);
-    const uint32_t a_lo_const = (plane_bytes >> 4) << 16;
+    const uint32_t a_lo_const = (((uint32_t)c.ndx * plane_bytes) >> 4) << 16;   // LBO: next 8-channel chunk
     const uint32_t b_lbo = (uint32_t)c.N_TILE * 16u;
     const uint32_t b_lo_const = (b_lbo >> 4) << 16;
-    const uint32_t a_step_t = ((uint32_t)chunks * plane_bytes) >> 4;
-    const uint32_t a_step_k = (2u * plane_bytes) >> 4;
+    const uint32_t a_step_t = ((uint32_t)(chunks * c.ndx) * plane_bytes) >> 4;
+    const uint32_t a_step_k = ((uint32_t)(2 * c.ndx) * plane_bytes) >> 4;
     const uint32_t b_step_sp = ((uint32_t)chunks * b_lbo) >> 4;
     const uint32_t b_step_k = (2u * b_lbo) >> 4;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -263,8 +268,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
           mbar_wait(b_full(sb.stage), sb.phase);
           tc_fence_after();
           if (elect_one()) {
-            const int shift = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
-            uint32_t a_lo = a_lo_const | ((a_stage + (uint32_t)(c.halo + shift) * 16u) >> 4);
+            const int dy = tap / 3 - 1, kx = tap % 3;
+            const uint32_t a_off = c.ndx == 3 ? (uint32_t)kx * plane_bytes + (uint32_t)(c.halo + dy * p.Wp) * 16u
+                                              : (uint32_t)(c.halo + dy * p.Wp + kx - 1) * 16u;
+            uint32_t a_lo = a_lo_const | ((a_stage + a_off) >> 4);
             const uint32_t b_lo0 = b_lo_const | ((b_base + sb.stage * c.b_stage_bytes) >> 4);
             uint32_t d = d_base;
             const uint32_t first = (kb | tap) != 0 ? 1u : 0u;
@@ -304,6 +311,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     int tau_exp;
     const bool tau_pow2 = frexpf(p.tau, &tau_exp) == 0.5f;
     const float inv_tau = 1.0f / p.tau;
+    const bool fast_lif = tau_pow2 && p.hard_reset && p.v_reset == 0.f;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n0 = (tile % c.n_tiles) * c.N_TILE;
       const int64_t r = (int64_t)(tile / c.n_tiles) * kTileRows + q * 32 + lane;  // padded row (without guard)
@@ -346,16 +354,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
             tc_ld16(t_base + (uint32_t)(t * c.N_TILE + cc), acc);
             tc_ld_wait();
             uint32_t packed[8];
+            if (fast_lif) {
+              // hard reset to 0, tau a power of two: h = v + (x - v) * (1/tau) is one exact-product FMA
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float x = fmaf(__uint_as_float(acc[j]), sc_[j], sh_[j]);
-              const float dv = p.hard_reset ? __fsub_rn(x, __fsub_rn(v[j], p.v_reset)) : __fsub_rn(x, v[j]);
-              const float h = __fadd_rn(v[j], tau_pow2 ? __fmul_rn(dv, inv_tau) : __fdiv_rn(dv, p.tau));
-              const bool s = h >= p.v_th;
-              v[j] = p.hard_reset ? (s ? p.v_reset : h) : (s ? __fsub_rn(h, p.v_th) : h);
-              cnt[j] += s ? 1.f : 0.f;
-              const uint32_t bits = s ? 0x3C00u : 0u;  // fp16 1.0
-              if (j & 1) packed[j >> 1] |= bits << 16; else packed[j >> 1] = bits;
+              for (int j = 0; j < 16; ++j) {
+                const float x = fmaf(__uint_as_float(acc[j]), sc_[j], sh_[j]);
+                const float h = fmaf(__fsub_rn(x, v[j]), inv_tau, v[j]);
+                const bool s = h >= p.v_th;
+                v[j] = s ? 0.f : h;
+                cnt[j] += s ? 1.f : 0.f;
+                const uint32_t bits = s ? 0x3C00u : 0u;  // fp16 1.0
+                if (j & 1) packed[j >> 1] |= bits << 16; else packed[j >> 1] = bits;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float x = fmaf(__uint_as_float(acc[j]), sc_[j], sh_[j]);
+                const float dv = p.hard_reset ? __fsub_rn(x, __fsub_rn(v[j], p.v_reset)) : __fsub_rn(x, v[j]);
+                const float h = __fadd_rn(v[j], tau_pow2 ? __fmul_rn(dv, inv_tau) : __fdiv_rn(dv, p.tau));
+                const bool s = h >= p.v_th;
+                v[j] = p.hard_reset ? (s ? p.v_reset : h) : (s ? __fsub_rn(h, p.v_th) : h);
+                cnt[j] += s ? 1.f : 0.f;
+                const uint32_t bits = s ? 0x3C00u : 0u;  // fp16 1.0
+                if (j & 1) packed[j >> 1] |= bits << 16; else packed[j >> 1] = bits;
+              }
             }
             if (valid && n < p.Cout && p.out_spk != nullptr) {
               __half* o = p.out_spk + (((int64_t)t * p.Cout8 + (n >> 3)) * p.R_alloc + p.G + r) * 8;
@@ -449,7 +471,9 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
   if (!tc_supported(d, &why)) { set_error("conv_tc: unsupported descriptor: %s", why); return SD_ERR_UNSUPPORTED; }
   c->T_acc = d->out_kind == SD_OUT_LIF ? d->T : 1;
   int n_tile;
-  if (c->T_acc * 128 * 2 <= 512) n_tile = 128;
+  // Larger N amortises the A-operand fetch from shared memory (4 KB per MMA whatever N is): measured on B200,
+  // N = 128 without epilogue overlap beats N = 64 with two TMEM stages (profiles/).
+  if (c->T_acc * 128 <= 512) n_tile = 128;
   else if (c->T_acc * 64 <= 512) n_tile = 64;
   else n_tile = 32;
   n_tile = env_int("SD_TC_NTILE", n_tile);
@@ -461,24 +485,35 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
   c->N_TILE = n_tile;
   c->acc_stages = 512 / (c->T_acc * n_tile) >= 2 ? 2 : 1;
   c->acc_stages = env_int("SD_TC_ACC_STAGES", c->acc_stages) >= 2 && 512 / (c->T_acc * n_tile) >= 2 ? 2 : 1;
-  c->halo = d->W_in + 2;
-  c->rows_ld = kTileRows + 2 * c->halo;
   const int c0 = d->C_in0, c1 = d->C_in - d->C_in0;
-  int kblk = env_int("SD_TC_KBLK", 32);
-  for (;; kblk /= 2) {
-    if (kblk < 16) { set_error("conv_tc: no K block fits shared memory"); return SD_ERR_UNSUPPORTED; }
-    if (!(kblk == 16 || kblk == 32 || kblk == 64)) continue;
-    if (c0 % kblk || c1 % kblk) continue;
-    c->a_stage_bytes = (uint32_t)c->T_acc * (kblk / 8) * c->rows_ld * 16;
-    c->b_stage_bytes = (uint32_t)d->nsplit * (kblk / 8) * n_tile * 16;
-    if (2 * c->a_stage_bytes + 3 * c->b_stage_bytes + 1024 <= kSmemBudget) break;
+  const int Wp = d->W_in + 1;
+  // Measured on B200 (profiles/r1_layer_sweep.txt): the pre-shifted (128-byte aligned) variant is SLOWER than plain
+  // 16-byte-aligned tap starts (its 3x larger A stage forces KBLK = 16), so it is opt-in only.
+  const int want_align = env_int("SD_TC_ALIGN", 0);
+  const int kblk_pref = env_int("SD_TC_KBLK", 0);
+  bool found = false;
+  for (int ndx = (want_align && Wp % 8 == 0) ? 3 : 1; ndx >= 1 && !found; ndx -= 2) {
+    c->ndx = ndx;
+    c->halo = ndx == 3 ? Wp : Wp + 1;
+    c->rows_ld = kTileRows + 2 * c->halo;
+    static const int kblks[3] = {64, 32, 16};
+    for (int i = 0; i < 3 && !found; ++i) {
+      const int kblk = kblks[i];
+      if (kblk_pref ? kblk != kblk_pref : (ndx == 1 && kblk == 64)) continue;   // default: 32 (then 16)
+      if (c0 % kblk || c1 % kblk) continue;
+      c->a_stage_bytes = (uint32_t)c->T_acc * (kblk / 8) * ndx * c->rows_ld * 16;
+      c->b_stage_bytes = (uint32_t)d->nsplit * (kblk / 8) * n_tile * 16;
+      if (2 * c->a_stage_bytes + 4 * c->b_stage_bytes + 1024 > kSmemBudget) continue;
+      c->KBLK = kblk;
+      found = true;
+    }
   }
-  c->KBLK = kblk;
-  // split the budget: B ring of 4 (one tap each), the rest to A (2..4 K blocks in flight)
-  c->b_stages = 4;
-  while (c->b_stages > 3 && 2 * c->a_stage_bytes + c->b_stages * c->b_stage_bytes + 1024 > kSmemBudget) --c->b_stages;
-  c->a_stages = (int)((kSmemBudget - 1024 - c->b_stages * c->b_stage_bytes) / c->a_stage_bytes);
+  if (!found) { set_error("conv_tc: no K block fits shared memory"); return SD_ERR_UNSUPPORTED; }
+  const int kblk = c->KBLK;
+  // A ring first (2..4 K blocks in flight), the rest of the budget to the B ring (one tap per stage)
+  c->a_stages = (int)((kSmemBudget - 1024 - 4 * c->b_stage_bytes) / c->a_stage_bytes);
   if (c->a_stages > kMaxAStages) c->a_stages = kMaxAStages;
+  if (c->a_stages > 3) c->a_stages = 3;
   uint32_t left = kSmemBudget - 1024 - c->a_stages * c->a_stage_bytes;
   c->b_stages = (int)(left / c->b_stage_bytes);
   if (c->b_stages > kMaxBStages) c->b_stages = kMaxBStages;

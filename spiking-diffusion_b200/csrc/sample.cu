@@ -59,6 +59,15 @@ __device__ __forceinline__ uint32_t philox_element(const PhiloxCall& c, uint64_t
   return ii == 0 ? r.x : (ii == 1 ? r.y : (ii == 2 ? r.z : r.w));
 }
 
+// Same draw when the caller already knows li = q * tpg + idx (no 64-bit division per element).
+__device__ __forceinline__ uint32_t philox_element_qr(const PhiloxCall& c, uint64_t q, uint32_t idx) {
+  const uint64_t ctr = c.offset4 + (q >> 2);
+  const uint32_t ii = (uint32_t)(q & 3);
+  uint4 r = Philox::round10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), idx, 0u),
+                            make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32)));
+  return ii == 0 ? r.x : (ii == 1 ? r.y : (ii == 2 ? r.z : r.w));
+}
+
 // torch.rand: value = rand*1 + 0, then the (0,1] -> [0,1) bound flip   (DistributionTemplates.h:493-503)
 __device__ __forceinline__ float torch_uniform(uint32_t raw) {
   float v = u32_to_uniform(raw);
@@ -148,6 +157,12 @@ __global__ void __launch_bounds__(256) sample_step_kernel(const float* __restric
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s2 = __fadd_rn(s2, __shfl_xor_sync(0xffffffffu, s2, off));
     // ---- multinomial(1) = argmax(probs / Exp(1)), first index on ties ----
+    // element index li = gtok*K + k = q*tpg + r: one 64-bit division per token, then r walks with at most one wrap
+    // per step (K <= tpg because tpg >= min(numel, 256) and K >= 128 divides numel)
+    const uint64_t li0 = (uint64_t)gtok * (uint64_t)K;
+    const uint64_t q0 = li0 / ce.tpg;
+    const uint32_t r0 = (uint32_t)(li0 - q0 * ce.tpg);
+    const uint32_t tpg32 = (uint32_t)ce.tpg;
     float best = -INFINITY;
     int besti = 0x7fffffff;
 #pragma unroll
@@ -155,7 +170,10 @@ __global__ void __launch_bounds__(256) sample_step_kernel(const float* __restric
       if (j < per_lane) {
         const int k = (j >> 2) * 128 + lane * 4 + (j & 3);
         const float p = __fdiv_rn(l[j], s2);
-        const float q = torch_exponential(philox_element(ce, (uint64_t)gtok * (uint64_t)K + (uint64_t)k));
+        uint32_t r = r0 + (uint32_t)k;
+        uint64_t qq = q0;
+        while (r >= tpg32) { r -= tpg32; ++qq; }
+        const float q = torch_exponential(philox_element_qr(ce, qq, r));
         const float val = __fdiv_rn(p, q);
         if (val > best || (val == best && k < besti)) { best = val; besti = k; }
       }
