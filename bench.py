@@ -255,7 +255,7 @@ def run_ours(args, wl, rank, world, local_rank):
     if world == 1 and not args.no_cpu_baseline:
         ips, cores, times, sample = cpu_reference_images_per_s(wl, args.cpu_batch, steps=1, warm_steps=2)
         cpu = {"value": round(ips, 4), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
-    launches = args.steps * (2 + steps_diff * 8 + 5 + 1)
+    launches = args.steps * (steps_diff * splan.kernel_launches_per_step + 5 + 1)
     line = {
         "metric": "generated images/sec", "value": round(value, 2), "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 3),
@@ -263,7 +263,8 @@ def run_ours(args, wl, rank, world, local_rank):
         "config": {"workload": f"{args.workload}: {wl['desc']}", "global_batch": n_global, "parallelism": f"batch-shard x{world}, no collective on the sampling path",
                    "temp": args.temp, "weight_split_terms": args.nsplit,
                    "timing": "CUDA events per step, max over ranks; L2 flushed (256 MiB write) between timed steps",
-                   "flop_per_image": int((splan.dp.flops() * steps_diff + vplan.flops()) // b)},
+                   "sampler_streams": len(splan.subs),
+                   "flop_per_image": int(splan.flops_per_image(steps_diff) + vplan.flops() // b)},
         "e2e": {"value": round(e2e, 2), "unit": "images/s", "h2d_bytes_per_step": int(x0_host.numel() * 8 + um_host.numel()),
                 "d2h_bytes_per_step": int(out_host.numel())},
         "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,

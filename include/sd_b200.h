@@ -22,12 +22,15 @@
  * Internal activation format ("spike tile format", STF), used between fused layers
  *   A spike tensor that is logically [T, B, C, H, W] is stored as fp16
  *       [T][C/8][R_alloc][8]          (8 channels = 16 bytes innermost)
- *   where rows enumerate a zero-padded pixel grid: Hp = H+1, Wp = W+1, P = Hp*Wp,
+ *   where rows enumerate the pixel grid with ONE zero pad column: Wp = W+1, P = H*Wp,
  *       row(b, y, x) = G + b*P + y*Wp + x,   0 <= y < H, 0 <= x < W,
- *   G = sd_stf_guard(W) leading guard rows, R_alloc = sd_stf_rows(B, H, W).  Pad rows (x == W or
- *   y == H) and guard rows are ALWAYS ZERO: buffers are zero-filled once by the caller and kernels
- *   only ever write valid rows.  With this layout a 3x3/stride-1/pad-1 convolution is nine
- *   row-shifted GEMMs over the same shared-memory tile (shift = dy*Wp + dx rows).
+ *   G = sd_stf_guard(W) leading guard rows, R_alloc = sd_stf_rows(B, H, W).  Pad rows (x == W) and guard
+ *   rows are ALWAYS ZERO: buffers are zero-filled once by the caller and kernels only ever write valid
+ *   rows.  With this layout a 3x3/stride-1/pad-1 convolution is nine row-shifted GEMMs over the same
+ *   shared-memory tile (shift = dy*Wp + dx rows): the pad column absorbs the horizontal wrap, and the
+ *   vertical wrap into the neighbouring image is cut by disabling those output rows in the dy = -1 / +1
+ *   MMAs (tcgen05.mma disable-output-lane mask), so no pad ROW is stored: 49 of 56 rows of a 7x7 grid
+ *   carry data.
  */
 #ifndef SD_B200_H_
 #define SD_B200_H_

@@ -5,14 +5,17 @@
 // which carry >99.9 % of the sampling FLOPs.
 //
 // GEMM view.  Activations live in the STF layout (include/sd_b200.h): per timestep and per 8-channel chunk a
-// plane of 16-byte rows, rows = zero-padded pixel grid flattened (Wp = W+1 columns, one shared zero row between
-// images).  For that layout the 3x3/stride-1/pad-1 convolution is nine GEMMs whose A operands are the SAME rows
-// shifted by dy*Wp + dx.  In shared memory the planes are exactly the tcgen05 "no-swizzle, K-major" canonical
-// layout (core matrix = 8 rows x 16 B contiguous, SBO = 128 B between 8-row groups, LBO = plane stride between
-// 8-channel chunks), so a tap is just a different 16-byte-aligned start address in the A descriptor: the input
-// tile is loaded ONCE per K-block and reused by all 9 taps (9x less L2->SMEM traffic than im2col).
+// plane of 16-byte rows, rows = pixel grid flattened with ONE zero pad column (Wp = W+1).  For that layout the
+// 3x3/stride-1/pad-1 convolution is nine GEMMs whose A operands are the SAME rows shifted by dy*Wp + dx: the pad
+// column absorbs the horizontal wrap; the vertical wrap into the neighbouring image is removed by masking the
+// affected OUTPUT rows of the dy = -1 / +1 MMAs (tcgen05.mma disable-output-lane mask), so 49 of every 56 rows of a
+// 7x7 grid are useful work (87.5 %; a stored pad row would make it 49/64).  In shared memory the planes are exactly
+// the tcgen05 "no-swizzle, K-major" canonical layout (core matrix = 8 rows x 16 B contiguous, SBO = 128 B between
+// 8-row groups, LBO = plane stride between 8-channel chunks), so a tap is just a different 16-byte-aligned start
+// address in the A descriptor: the input tile is loaded ONCE per K-block and reused by all 9 taps (9x less
+// L2->SMEM traffic than im2col).
 //
-//   M tile  = 128 consecutive padded rows (2 images of a 7x7 grid), all T timesteps
+//   M tile  = 128 consecutive rows of the flat pixel sequence (tiles may straddle images), all T timesteps
 //   N tile  = 32..128 output channels
 //   K block = 16..64 input channels, x 9 taps, x nsplit fp16 weight terms
 //   D       = T accumulators of [128 x N] fp32 resident in TMEM (T*N <= 512 columns, x2 stages when they fit)
@@ -119,6 +122,19 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
       "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with a disable-output-lane mask: bit i of the 128-bit mask set => row i of D is neither written nor
+// accumulated by this MMA.
+__device__ __forceinline__ void tc_mma_f16_masked(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                  uint32_t accumulate, uint32_t m0, uint32_t m1, uint32_t m2,
+                                                  uint32_t m3) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -148,6 +164,10 @@ __device__ __forceinline__ bool elect_one() {
       : "r"(0xFFFFFFFFu));
   return pred != 0;
 }
+
+// Taps are visited centre row first (dy = 0, then -1, then +1): the first MMA of a tile overwrites the accumulator
+// (accumulate = 0) and must therefore have every output row enabled; the dy != 0 taps mask rows at the image border.
+__device__ __forceinline__ int tap_order(int i) { return i < 3 ? i + 3 : (i < 6 ? i - 3 : i); }
 
 struct PipeState {
   int stage = 0;
@@ -235,10 +255,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
       const int n_tile = tile % c.n_tiles;
       const __half* wsrc = p.wpack + (int64_t)n_tile * c.num_kblocks * 9 * stage_halfs;
       for (int it = 0; it < c.num_kblocks * 9; ++it) {
+        const int kb = it / 9, tap = tap_order(it - kb * 9);
         mbar_wait(b_empty(st.stage), st.phase ^ 1);
         if (elect_one()) {
           mbar_expect_tx(b_full(st.stage), c.b_stage_bytes);
-          bulk_g2s(b_base + st.stage * c.b_stage_bytes, wsrc + (int64_t)it * stage_halfs, c.b_stage_bytes,
+          bulk_g2s(b_base + st.stage * c.b_stage_bytes, wsrc + (int64_t)(kb * 9 + tap) * stage_halfs, c.b_stage_bytes,
                    b_full(st.stage));
         }
         __syncwarp();
@@ -261,10 +282,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
       mbar_wait(acc_empty(sc.stage), sc.phase ^ 1);
       tc_fence_after();
       const uint32_t d_base = tmem_base + (uint32_t)(sc.stage * c.T_acc * c.N_TILE);
+      // rows of this tile at the top (y == 0) / bottom (y == H-1) of their image: disabled for dy = -1 / +1
+      uint32_t m_up[4], m_dn[4];
+      {
+        const int64_t row0 = (int64_t)(tile / c.n_tiles) * kTileRows;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const int y = (int)((row0 + w * 32 + lane) % p.P) / p.Wp;
+          m_up[w] = __ballot_sync(0xffffffffu, y == 0);
+          m_dn[w] = __ballot_sync(0xffffffffu, y == p.H - 1);
+        }
+      }
       for (int kb = 0; kb < c.num_kblocks; ++kb) {
         mbar_wait(a_full(sa.stage), sa.phase);
         const uint32_t a_stage = a_base + sa.stage * c.a_stage_bytes;
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int ti = 0; ti < 9; ++ti) {
+          const int tap = tap_order(ti);
           mbar_wait(b_full(sb.stage), sb.phase);
           tc_fence_after();
           if (elect_one()) {
@@ -274,7 +307,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
             uint32_t a_lo = a_lo_const | ((a_stage + a_off) >> 4);
             const uint32_t b_lo0 = b_lo_const | ((b_base + sb.stage * c.b_stage_bytes) >> 4);
             uint32_t d = d_base;
-            const uint32_t first = (kb | tap) != 0 ? 1u : 0u;
+            const uint32_t first = (kb | ti) != 0 ? 1u : 0u;
+            const uint32_t k0 = dy == 0 ? 0u : (dy < 0 ? m_up[0] : m_dn[0]), k1 = dy == 0 ? 0u : (dy < 0 ? m_up[1] : m_dn[1]);
+            const uint32_t k2 = dy == 0 ? 0u : (dy < 0 ? m_up[2] : m_dn[2]), k3 = dy == 0 ? 0u : (dy < 0 ? m_up[3] : m_dn[3]);
             for (int t = 0; t < c.T_acc; ++t) {
 #pragma unroll
               for (int sp = 0; sp < NSPLIT; ++sp) {
@@ -282,14 +317,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
                 for (int ks = 0; ks < KSTEPS; ++ks) {
                   const uint64_t adesc = ((uint64_t)desc_hi << 32) | (a_lo + ks * a_step_k);
                   const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (b_lo0 + sp * b_step_sp + ks * b_step_k);
-                  tc_mma_f16(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first);
+                  tc_mma_f16_masked(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first, k0, k1, k2, k3);
                 }
               }
               a_lo += a_step_t;
               d += (uint32_t)c.N_TILE;
             }
             tc_commit(b_empty(sb.stage));
-            if (tap == 8) tc_commit(a_empty(sa.stage));
+            if (ti == 8) tc_commit(a_empty(sa.stage));
           }
           __syncwarp();
           sb.advance(c.b_stages);
@@ -317,7 +352,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
       const int64_t r = (int64_t)(tile / c.n_tiles) * kTileRows + q * 32 + lane;  // padded row (without guard)
       const int pp = (int)(r % p.P);
       const int py = pp / p.Wp, px = pp - py * p.Wp;
-      const bool valid = (r < p.R_valid) && (px < p.W) && (py < p.H);
+      const bool valid = (r < p.R_valid) && (px < p.W);
       mbar_wait(acc_full(sc.stage), sc.phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc.stage * c.T_acc * c.N_TILE);
@@ -519,7 +554,7 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
   if (c->b_stages > kMaxBStages) c->b_stages = kMaxBStages;
   c->smem_bytes = 1024 + c->a_stages * c->a_stage_bytes + c->b_stages * c->b_stage_bytes;
   c->n_tiles = (d->C_out + n_tile - 1) / n_tile;
-  const int64_t R = (int64_t)d->B * (d->H_in + 1) * (d->W_in + 1);
+  const int64_t R = (int64_t)d->B * d->H_in * (d->W_in + 1);
   c->m_tiles = (int)((R + kTileRows - 1) / kTileRows);
   c->c0_blocks = c0 / kblk;
   c->num_kblocks = c0 / kblk + c1 / kblk;

@@ -102,9 +102,12 @@ __global__ void philox_fill_kernel(float* __restrict__ out, int64_t numel, int64
   }
 }
 
-// One warp per token.  K is a multiple of 32; each lane keeps K/32 logits in registers (K <= 1024).
-constexpr int kMaxPerLane = 32;
+// One warp per token.  K is a multiple of 128; each lane keeps K/32 logits in registers (K <= 1024).
+// Templated on the register-array size so that K = 128 compiles to a compact loop (the 32-wide unroll is ~100 KB of
+// code and thrashes the instruction cache when only 4 of its 32 iterations execute).
+constexpr int kMaxPerLaneAll = 32;
 
+template <int kMaxPerLane>
 __global__ void __launch_bounds__(256) sample_step_kernel(const float* __restrict__ logits, int64_t* __restrict__ x_t,
                                                           uint8_t* __restrict__ unmasked, int64_t* __restrict__ x0_hat,
                                                           int64_t n_tokens, int K, float inv_t, float inv_temp,
@@ -255,8 +258,8 @@ int sd_sample_step(const float* logits, int64_t* x_t, uint8_t* unmasked, int64_t
                    int t, float temp, uint64_t seed, uint64_t offset_uniform, uint64_t offset_exponential,
                    int64_t token_base, int64_t n_tokens_global, void* stream) {
   SD_REQUIRE(n_tokens >= 0 && token_base >= 0 && n_tokens_global >= token_base + n_tokens, "sample_step: bad token range");
-  SD_REQUIRE(K >= 32 && K % 128 == 0 && K <= 32 * kMaxPerLane, "sample_step: K=%d must be a multiple of 128 in [128, %d]", K,
-             32 * kMaxPerLane);
+  SD_REQUIRE(K >= 32 && K % 128 == 0 && K <= 32 * kMaxPerLaneAll, "sample_step: K=%d must be a multiple of 128 in [128, %d]", K,
+             32 * kMaxPerLaneAll);
   SD_REQUIRE(t >= 1, "sample_step: t must be >= 1");
   SD_REQUIRE(temp > 0.f, "sample_step: temperature must be positive");
   SD_REQUIRE(offset_uniform % 4 == 0 && offset_exponential % 4 == 0, "sample_step: offsets must be multiples of 4");
@@ -272,8 +275,14 @@ int sd_sample_step(const float* logits, int64_t* x_t, uint8_t* unmasked, int64_t
   ce.offset4 = offset_exponential / 4;
   const float inv_t = 1.0f / (float)t;  // `1 / t_mask.float()`  (vq_diffusion.py:118)
   int64_t blocks = (n_tokens * 32 + 255) / 256;
-  sample_step_kernel<<<grid_cap(blocks), 256, 0, as_stream(stream)>>>(logits, x_t, unmasked, x0_hat, n_tokens, K, inv_t,
-                                                                      1.0f / temp, cu, ce, token_base);
+#define SD_SAMPLE_LAUNCH(PL)                                                                                  \
+  sample_step_kernel<PL><<<grid_cap(blocks), 256, 0, as_stream(stream)>>>(logits, x_t, unmasked, x0_hat, n_tokens, K, \
+                                                                          inv_t, 1.0f / temp, cu, ce, token_base)
+  if (K <= 128) SD_SAMPLE_LAUNCH(4);
+  else if (K <= 256) SD_SAMPLE_LAUNCH(8);
+  else if (K <= 512) SD_SAMPLE_LAUNCH(16);
+  else SD_SAMPLE_LAUNCH(32);
+#undef SD_SAMPLE_LAUNCH
   SD_LAUNCH_CHECK();
   return SD_OK;
 }

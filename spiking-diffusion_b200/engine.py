@@ -70,7 +70,7 @@ class FusedLayer:
 
     def __init__(self, conv, bn, lif, *, T: int, B: int, H_in: int, W_in: int, in_kind: int, out_kind: int,
                  impl: str = "auto", nsplit: int = 2, in_T: Optional[int] = None, C_in0: Optional[int] = None,
-                 memout_coef: Optional[torch.Tensor] = None):
+                 memout_coef: Optional[torch.Tensor] = None, share: Optional["FusedLayer"] = None):
         L = lib()
         w = conv.weight.detach()
         _require_cuda(w, "layer weights")
@@ -115,6 +115,12 @@ class FusedLayer:
         if impl == "tc" and not L.sd_conv_tc_supported(ctypes.byref(d)):
             raise ValueError("layer is not supported by the tcgen05 kernel: " + L.sd_last_error().decode())
         self.impl = impl
+        self._fn = L.sd_conv_lif_tc if impl == "tc" else L.sd_conv_lif_simt
+        self._coef = None
+        if share is not None and share.impl == impl and share.desc.nsplit == nsplit and share.T == T:
+            # packed weights do not depend on the batch size: sub-batch plans reuse them
+            self.wpack, self.scale, self.shift, self._coef = share.wpack, share.scale, share.shift, share._coef
+            return
         scale, shift = fold_bn(conv.bias, C_out, bn, self.device)
         wsrc = w.float().contiguous()
         if impl == "tc":
@@ -128,12 +134,10 @@ class FusedLayer:
             self.wpack = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             check(L.sd_conv_pack_weights_simt(ctypes.byref(d), ptr(wsrc), ptr(self.wpack), stream_ptr()))
         self.scale, self.shift = scale, shift
-        self._coef = None
         if out_kind == _lib.OUT_MEMOUT_TANH:
             if memout_coef is None:
                 raise ValueError("memout_coef required for the memout+tanh tail")
             self._coef = (ctypes.c_float * T)(*[float(v) for v in memout_coef.detach().reshape(-1).cpu().tolist()[:T]])
-        self._fn = L.sd_conv_lif_tc if impl == "tc" else L.sd_conv_lif_simt
 
     def flops(self) -> int:
         """Dense algorithmic FLOPs (2*MAC) of one call, counted as SURVEY.md section 8(d) does."""
@@ -180,20 +184,22 @@ class DenoiserPlan:
     """DummyModel.forward for a fixed (T, b, h, w): conv1 (real, constant over T) on CUDA cores, conv2..conv5 as
     fused tcgen05 conv+BN+LIF, conv6 on the T-summed spikes of cat(x5, x1) (linear read-out, mean over T)."""
 
-    def __init__(self, model, T: int, b: int, h: int, w: int, nsplit: int = 2, impl: str = "auto"):
+    def __init__(self, model, T: int, b: int, h: int, w: int, nsplit: int = 2, impl: str = "auto",
+                 weights_from: Optional["DenoiserPlan"] = None):
         dev = model.conv1[0].weight.device
         _require_cuda(model.conv1[0].weight, "DummyModel parameters")
         self.T, self.b, self.h, self.w, self.K = T, b, h, w, model.num_embeddings
         self.device = dev
-        mk = lambda seq, **kw: FusedLayer(seq[0], seq[1] if len(seq) > 1 else None, seq[2] if len(seq) > 2 else None,
-                                          T=T, B=b, H_in=h, W_in=w, nsplit=nsplit, **kw)
-        self.l1 = mk(model.conv1, in_kind=_lib.IN_REAL_CONST, out_kind=_lib.OUT_LIF, impl="simt")
-        self.l2 = mk(model.conv2, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
-        self.l3 = mk(model.conv3, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
-        self.l4 = mk(model.conv4, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
-        self.l5 = mk(model.conv5, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
-        self.l6 = mk(model.conv6, in_kind=_lib.IN_STF, out_kind=_lib.OUT_MEAN_T, impl=impl, in_T=1,
-                     C_in0=self.l5.C_out)
+        wf = weights_from
+        mk = lambda seq, sh, **kw: FusedLayer(seq[0], seq[1] if len(seq) > 1 else None, seq[2] if len(seq) > 2 else None,
+                                              T=T, B=b, H_in=h, W_in=w, nsplit=nsplit, share=sh, **kw)
+        self.l1 = mk(model.conv1, wf and wf.l1, in_kind=_lib.IN_REAL_CONST, out_kind=_lib.OUT_LIF, impl="simt")
+        self.l2 = mk(model.conv2, wf and wf.l2, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
+        self.l3 = mk(model.conv3, wf and wf.l3, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
+        self.l4 = mk(model.conv4, wf and wf.l4, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
+        self.l5 = mk(model.conv5, wf and wf.l5, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
+        self.l6 = mk(model.conv6, wf and wf.l6, in_kind=_lib.IN_STF, out_kind=_lib.OUT_MEAN_T, impl=impl, in_T=1,
+                     C_in0=256)
         self.layers = [self.l1, self.l2, self.l3, self.l4, self.l5, self.l6]
         self.xin = torch.empty((b, 2, h, w), dtype=torch.float32, device=dev)
         self.x1, self.x1s = self.l1.alloc_out(), self.l1.alloc_sum()
@@ -231,33 +237,64 @@ class SamplerPlan:
     Philox stream: step i draws its uniforms at generator offset ``offset0 + i*(inc_u + inc_e)`` and its
     exponentials at ``+ inc_u``, exactly what two consecutive torch CUDA calls (rand_like, exponential_) consume for
     the GLOBAL batch; a shard [token_base, token_base + n) evaluates only its own elements of that stream.
+
+    Sub-batches and streams: images are independent, so the shard is cut into ``n_streams`` sub-batches whose whole
+    reverse-diffusion loops run on separate CUDA streams.  Each fused layer is a persistent kernel with one CTA per
+    SM; with a single stream the last, partially filled wave of every layer idles SMs (112 M-tiles x 4 N-tiles on
+    148 SMs = 3.03 waves).  With two streams the tail of one sub-batch's layer overlaps the head of the other's.
     """
 
-    def __init__(self, denoiser_plan: DenoiserPlan, mask_id: int, n_global: Optional[int] = None, shard_base: int = 0):
-        self.dp = denoiser_plan
+    def __init__(self, model, T: int, b: int, h: int, w: int, mask_id: int, n_global: Optional[int] = None,
+                 shard_base: int = 0, n_streams: Optional[int] = None, nsplit: int = 2):
+        import os
+        if n_streams is None:
+            n_streams = int(os.environ.get("SD_SAMPLER_STREAMS", "2"))
+        n_streams = max(1, min(n_streams, b))
         self.mask_id = int(mask_id)
-        dp = denoiser_plan
-        self.n_tokens = dp.b * dp.h * dp.w
-        self.n_tokens_global = (n_global if n_global is not None else dp.b) * dp.h * dp.w
-        self.token_base = shard_base * dp.h * dp.w
-        self.x_t = torch.empty(self.n_tokens, dtype=torch.int64, device=dp.device)
-        self.unmasked = torch.empty(self.n_tokens, dtype=torch.uint8, device=dp.device)
+        self.b, self.h, self.w, self.K = b, h, w, model.num_embeddings
+        hw = h * w
+        self.n_tokens = b * hw
+        self.n_tokens_global = (n_global if n_global is not None else b) * hw
+        self.token_base = shard_base * hw
+        dev = model.conv1[0].weight.device
+        self.x_t = torch.empty(self.n_tokens, dtype=torch.int64, device=dev)
+        self.unmasked = torch.empty(self.n_tokens, dtype=torch.uint8, device=dev)
+        self.subs = []
+        per = (b + n_streams - 1) // n_streams
+        lo = 0
+        while lo < b:
+            bi = min(per, b - lo)
+            # each sub-batch has its own activation buffers (they run concurrently) but shares the packed weights
+            dp = DenoiserPlan(model, T, bi, h, w, nsplit=nsplit, weights_from=self.subs[0][0] if self.subs else None)
+            self.subs.append((dp, lo, bi))
+            lo += bi
+        self.dp = self.subs[0][0]
+        self.streams = [torch.cuda.Stream(device=dev) for _ in self.subs] if len(self.subs) > 1 else [None]
         inc = ctypes.c_uint64()
         check(lib().sd_philox_offset_increment(self.n_tokens_global, ctypes.byref(inc)))
         self.inc_u = inc.value
-        check(lib().sd_philox_offset_increment(self.n_tokens_global * dp.K, ctypes.byref(inc)))
+        check(lib().sd_philox_offset_increment(self.n_tokens_global * self.K, ctypes.byref(inc)))
         self.inc_e = inc.value
-        self.kernel_launches_per_step = 8
+        self.kernel_launches_per_step = 8 * len(self.subs)
+
+    def flops_per_image(self, sample_steps: int) -> int:
+        return sum(dp.flops() for dp, _, _ in self.subs) * sample_steps // self.b
 
     def offset_advance(self, sample_steps: int) -> int:
         return sample_steps * (self.inc_u + self.inc_e)
+
+    def _step(self, dp, lo, bi, t, temp, seed, off):
+        hw = self.h * self.w
+        xs = self.x_t[lo * hw:(lo + bi) * hw]
+        us = self.unmasked[lo * hw:(lo + bi) * hw]
+        logits = dp.run_tokens(xs, t)
+        check(lib().sd_sample_step(ptr(logits), ptr(xs), ptr(us), None, bi * hw, self.K, t, float(temp), int(seed), off,
+                                   off + self.inc_u, self.token_base + lo * hw, self.n_tokens_global, stream_ptr()))
 
     def sample(self, temp: float, sample_steps: int, seed: int, offset0: int = 0,
                x_init: Optional[torch.Tensor] = None, unmasked_init: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x_init / unmasked_init (host or device, [b,1,h,w] or flat): start from a partially unmasked grid
         instead of the all-mask grid of vq_diffusion.py:106-107; copied on the current stream (pinned host -> device)."""
-        dp = self.dp
-        L = lib()
         if x_init is None:
             self.x_t.fill_(self.mask_id)
         else:
@@ -266,14 +303,28 @@ class SamplerPlan:
             self.unmasked.zero_()
         else:
             self.unmasked.copy_(unmasked_init.reshape(-1), non_blocking=True)
+        multi = len(self.subs) > 1
+        if multi:
+            cur = torch.cuda.current_stream()
+            start = torch.cuda.Event()
+            start.record(cur)
+            for s in self.streams:
+                s.wait_event(start)
         off = int(offset0)
         for t in range(sample_steps, 0, -1):
-            logits = dp.run_tokens(self.x_t, t)
-            check(L.sd_sample_step(ptr(logits), ptr(self.x_t), ptr(self.unmasked), None, self.n_tokens, dp.K, t,
-                                   float(temp), int(seed), off, off + self.inc_u, self.token_base,
-                                   self.n_tokens_global, stream_ptr()))
+            for (dp, lo, bi), s in zip(self.subs, self.streams):
+                if multi:
+                    with torch.cuda.stream(s):
+                        self._step(dp, lo, bi, t, temp, seed, off)
+                else:
+                    self._step(dp, lo, bi, t, temp, seed, off)
             off += self.inc_u + self.inc_e
-        return self.x_t.view(dp.b, 1, dp.h, dp.w)
+        if multi:
+            for s in self.streams:
+                done = torch.cuda.Event()
+                done.record(s)
+                cur.wait_event(done)
+        return self.x_t.view(self.b, 1, self.h, self.w)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -107,10 +107,13 @@ class AbsorbingDiffusion(Sampler):
 
     def plan(self, b: int, n_global=None, shard_base: int = 0) -> "engine.SamplerPlan":
         h, w = self.shape
-        dp = self._denoise_fn.plan(b, h, w)
-        key = (id(dp), int(self.mask_id), n_global, shard_base)
+        m = self._denoise_fn
+        key = (b, h, w, m.T, m.nsplit, int(self.mask_id), n_global, shard_base,
+               tuple(p._version for p in m.parameters()), tuple(bf._version for bf in m.buffers()),
+               next(m.parameters()).device)
         if self._plans.get("key") != key:
-            self._plans = {"key": key, "plan": engine.SamplerPlan(dp, int(self.mask_id), n_global, shard_base)}
+            self._plans = {"key": key, "plan": engine.SamplerPlan(m, m.T, b, h, w, int(self.mask_id), n_global,
+                                                                  shard_base, nsplit=m.nsplit)}
         return self._plans["plan"]
 
     @torch.no_grad()

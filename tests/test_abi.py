@@ -43,9 +43,9 @@ def test_geometry_queries_are_host_only():
     L = _lib.lib()
     assert L.sd_version() == 1
     assert L.sd_stf_guard(7) == 16 and L.sd_stf_guard(28) == 32
-    # 256 images of an 8x8 padded grid = 16384 rows = 128 tiles of 128, + 2 guards
-    assert L.sd_stf_rows(256, 7, 7) == 16384 + 32
-    assert L.sd_stf_bytes(4, 256, 64, 7, 7) == 4 * 8 * (16384 + 32) * 8 * 2
+    # 256 images x 7 rows x (7+1 pad column) = 14336 rows = 112 tiles of 128, + 2 guards of 16
+    assert L.sd_stf_rows(256, 7, 7) == 14336 + 32
+    assert L.sd_stf_bytes(4, 256, 64, 7, 7) == 4 * 8 * (14336 + 32) * 8 * 2
     assert L.sd_stf_bytes(1, 1, 3, 7, 7) == 1 * 1 * (128 + 32) * 8 * 2  # C rounded up to 8
 
 
