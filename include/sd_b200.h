@@ -22,15 +22,15 @@
  * Internal activation format ("spike tile format", STF), used between fused layers
  *   A spike tensor that is logically [T, B, C, H, W] is stored as fp16
  *       [T][C/8][R_alloc][8]          (8 channels = 16 bytes innermost)
- *   where rows enumerate the pixel grid with ONE zero pad column: Wp = W+1, P = H*Wp,
- *       row(b, y, x) = G + b*P + y*Wp + x,   0 <= y < H, 0 <= x < W,
- *   G = sd_stf_guard(W) leading guard rows, R_alloc = sd_stf_rows(B, H, W).  Pad rows (x == W) and guard
- *   rows are ALWAYS ZERO: buffers are zero-filled once by the caller and kernels only ever write valid
- *   rows.  With this layout a 3x3/stride-1/pad-1 convolution is nine row-shifted GEMMs over the same
- *   shared-memory tile (shift = dy*Wp + dx rows): the pad column absorbs the horizontal wrap, and the
- *   vertical wrap into the neighbouring image is cut by disabling those output rows in the dy = -1 / +1
- *   MMAs (tcgen05.mma disable-output-lane mask), so no pad ROW is stored: 49 of 56 rows of a 7x7 grid
- *   carry data.
+ *   where rows enumerate the pixels densely, P = H*W rows per image,
+ *       row(b, y, x) = G + b*P + y*W + x,
+ *   G = sd_stf_guard(W) zero guard rows before and after, R_alloc = sd_stf_rows(B, H, W) (rounded up to a
+ *   multiple of 128 rows + 2 guards).  Guard rows and the tail are ALWAYS ZERO: buffers are zero-filled
+ *   once by the caller and kernels only ever write valid rows.  With this layout a 3x3/stride-1/pad-1
+ *   convolution is nine row-shifted GEMMs over the same shared-memory tile (shift = dy*W + dx rows); the
+ *   rows whose shifted source would wrap across an image border (y == 0 for dy = -1, x == W-1 for dx = +1,
+ *   ...) are excluded per tap with the tcgen05.mma disable-output-lane mask, so no padding is stored and
+ *   every row of an M tile is useful work.
  */
 #ifndef SD_B200_H_
 #define SD_B200_H_
@@ -208,6 +208,15 @@ int sd_philox_offset_increment(int64_t numel_global, uint64_t* inc_out);
 int sd_sample_step(const float* logits, int64_t* x_t, uint8_t* unmasked, int64_t* x0_hat_or_null,
                    int64_t n_tokens, int K, int t, float temp, uint64_t seed, uint64_t offset_uniform,
                    uint64_t offset_exponential, int64_t token_base, int64_t n_tokens_global, void* stream);
+
+/* Same step with (seed, base generator offset) read from DEVICE memory (rng_dev[0] = seed, rng_dev[1] = offset, a
+ * multiple of 4) and the two per-step offsets given relative to that base: the launch parameters are then
+ * independent of the RNG state, so a CUDA graph of the whole sampling loop can be replayed with a new stream by
+ * rewriting 16 bytes of device memory. */
+int sd_sample_step_dev(const float* logits, int64_t* x_t, uint8_t* unmasked, int64_t* x0_hat_or_null,
+                       int64_t n_tokens, int K, int t, float temp, const uint64_t* rng_dev,
+                       uint64_t rel_offset_uniform, uint64_t rel_offset_exponential, int64_t token_base,
+                       int64_t n_tokens_global, void* stream);
 
 /* Builds the denoiser's first-layer input cat(x_t as float, t) (R/snn_model/vq_diffusion.py:195-196):
  * x_t int64 [B*H*W] -> fp32 [B, 2, H, W]. */

@@ -26,7 +26,7 @@ SYMBOLS = [
     "sd_stf_from_nchw", "sd_stf_to_nchw", "sd_channel_affine", "sd_state_convert", "sd_lif_forward", "sd_memout", "sd_vq_feature", "sd_vq_lookup",
     "sd_vq_gather", "sd_conv_weight_bytes_simt", "sd_conv_weight_bytes_tc", "sd_conv_pack_weights_simt",
     "sd_conv_pack_weights_tc", "sd_conv_lif_simt", "sd_conv_lif_tc", "sd_conv_tc_supported", "sd_philox_uniform",
-    "sd_philox_exponential", "sd_philox_offset_increment", "sd_sample_step", "sd_denoiser_input", "sd_to_uint8",
+    "sd_philox_exponential", "sd_philox_offset_increment", "sd_sample_step", "sd_sample_step_dev", "sd_denoiser_input", "sd_to_uint8",
 ]
 
 
@@ -127,6 +127,7 @@ def _declare(lib: ctypes.CDLL) -> None:
         "sd_philox_exponential": (i, [vp, i64, u64, u64, i64, i64, ctypes.POINTER(u64), vp]),
         "sd_philox_offset_increment": (i, [i64, ctypes.POINTER(u64)]),
         "sd_sample_step": (i, [vp, vp, vp, vp, i64, i, i, f, u64, u64, u64, i64, i64, vp]),
+        "sd_sample_step_dev": (i, [vp, vp, vp, vp, i64, i, i, f, vp, u64, u64, i64, i64, vp]),
         "sd_denoiser_input": (i, [vp, vp, i, i, i, i, vp]),
         "sd_to_uint8": (i, [vp, vp, i64, vp]),
     }

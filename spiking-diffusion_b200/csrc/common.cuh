@@ -51,11 +51,11 @@ int validate_conv_desc(const sd_conv_desc* d);  // SD_OK or SD_ERR_INVALID (conv
 constexpr int kTileRows = 128;  // M of one tcgen05 tile
 
 __host__ __device__ inline int64_t stf_guard(int W) {
-  int64_t g = (int64_t)W + 2;           // >= Wp + 1, the largest row shift of a 3x3 window
+  int64_t g = (int64_t)W + 1;           // the largest row shift of a 3x3 window
   return (g + 7) / 8 * 8;
 }
 __host__ __device__ inline int64_t stf_rows(int B, int H, int W) {
-  int64_t P = (int64_t)H * (W + 1);
+  int64_t P = (int64_t)H * W;
   int64_t R = (int64_t)B * P;
   R = (R + kTileRows - 1) / kTileRows * kTileRows;
   return stf_guard(W) * 2 + R;
@@ -66,7 +66,7 @@ struct StfGeom {
   int H, W, Wp, P;
   int64_t G, R_alloc;
   __host__ __device__ StfGeom(int B, int H_, int W_)
-      : H(H_), W(W_), Wp(W_ + 1), P(H_ * (W_ + 1)), G(stf_guard(W_)), R_alloc(stf_rows(B, H_, W_)) {}
+      : H(H_), W(W_), Wp(W_), P(H_ * W_), G(stf_guard(W_)), R_alloc(stf_rows(B, H_, W_)) {}
   __host__ __device__ int64_t row(int b, int y, int x) const { return G + (int64_t)b * P + y * Wp + x; }
   // half index of (t, c, row) for a tensor with C8 channel chunks
   __host__ __device__ int64_t at(int t, int C8, int c, int64_t r) const {

@@ -5,15 +5,15 @@
 // which carry >99.9 % of the sampling FLOPs.
 //
 // GEMM view.  Activations live in the STF layout (include/sd_b200.h): per timestep and per 8-channel chunk a
-// plane of 16-byte rows, rows = pixel grid flattened with ONE zero pad column (Wp = W+1).  For that layout the
-// 3x3/stride-1/pad-1 convolution is nine GEMMs whose A operands are the SAME rows shifted by dy*Wp + dx: the pad
-// column absorbs the horizontal wrap; the vertical wrap into the neighbouring image is removed by masking the
-// affected OUTPUT rows of the dy = -1 / +1 MMAs (tcgen05.mma disable-output-lane mask), so 49 of every 56 rows of a
-// 7x7 grid are useful work (87.5 %; a stored pad row would make it 49/64).  In shared memory the planes are exactly
-// the tcgen05 "no-swizzle, K-major" canonical layout (core matrix = 8 rows x 16 B contiguous, SBO = 128 B between
-// 8-row groups, LBO = plane stride between 8-channel chunks), so a tap is just a different 16-byte-aligned start
-// address in the A descriptor: the input tile is loaded ONCE per K-block and reused by all 9 taps (9x less
-// L2->SMEM traffic than im2col).
+// plane of 16-byte rows, rows = the pixels of all images flattened densely (H*W rows per image, no padding).  For
+// that layout the 3x3/stride-1/pad-1 convolution is nine GEMMs whose A operands are the SAME rows shifted by
+// dy*W + dx.  A shifted row that would cross an image border (the zero padding of the convolution) is removed by
+// masking the affected OUTPUT rows of that tap's MMAs with the tcgen05.mma disable-output-lane mask (y == 0 for
+// dy = -1, y == H-1 for dy = +1, x == 0 for dx = -1, x == W-1 for dx = +1), so every row of an M tile is useful
+// work.  In shared memory the planes are exactly the tcgen05 "no-swizzle, K-major" canonical layout (core matrix =
+// 8 rows x 16 B contiguous, SBO = 128 B between 8-row groups, LBO = plane stride between 8-channel chunks), so a tap
+// is just a different 16-byte-aligned start address in the A descriptor: the input tile is loaded ONCE per K-block
+// and reused by all 9 taps (9x less L2->SMEM traffic than im2col).
 //
 //   M tile  = 128 consecutive rows of the flat pixel sequence (tiles may straddle images), all T timesteps
 //   N tile  = 32..128 output channels
@@ -165,9 +165,9 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// Taps are visited centre row first (dy = 0, then -1, then +1): the first MMA of a tile overwrites the accumulator
-// (accumulate = 0) and must therefore have every output row enabled; the dy != 0 taps mask rows at the image border.
-__device__ __forceinline__ int tap_order(int i) { return i < 3 ? i + 3 : (i < 6 ? i - 3 : i); }
+// The centre tap is visited first: the first MMA of a tile overwrites the accumulator (accumulate = 0) and must
+// therefore have every output row enabled; all other taps mask the rows at the image border they would cross.
+__device__ __forceinline__ int tap_order(int i) { return i == 0 ? 4 : (i <= 4 ? i - 1 : i); }
 
 struct PipeState {
   int stage = 0;
@@ -282,15 +282,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
       mbar_wait(acc_empty(sc.stage), sc.phase ^ 1);
       tc_fence_after();
       const uint32_t d_base = tmem_base + (uint32_t)(sc.stage * c.T_acc * c.N_TILE);
-      // rows of this tile at the top (y == 0) / bottom (y == H-1) of their image: disabled for dy = -1 / +1
-      uint32_t m_up[4], m_dn[4];
+      // rows of this tile on the top / bottom / left / right border of their image: the taps that would read across
+      // that border have these output rows disabled
+      uint32_t m_up[4], m_dn[4], m_lf[4], m_rt[4];
       {
         const int64_t row0 = (int64_t)(tile / c.n_tiles) * kTileRows;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-          const int y = (int)((row0 + w * 32 + lane) % p.P) / p.Wp;
+          const int pp = (int)((row0 + w * 32 + lane) % p.P);
+          const int y = pp / p.W, x = pp - y * p.W;
           m_up[w] = __ballot_sync(0xffffffffu, y == 0);
           m_dn[w] = __ballot_sync(0xffffffffu, y == p.H - 1);
+          m_lf[w] = __ballot_sync(0xffffffffu, x == 0);
+          m_rt[w] = __ballot_sync(0xffffffffu, x == p.W - 1);
         }
       }
       for (int kb = 0; kb < c.num_kblocks; ++kb) {
@@ -308,8 +312,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
             const uint32_t b_lo0 = b_lo_const | ((b_base + sb.stage * c.b_stage_bytes) >> 4);
             uint32_t d = d_base;
             const uint32_t first = (kb | ti) != 0 ? 1u : 0u;
-            const uint32_t k0 = dy == 0 ? 0u : (dy < 0 ? m_up[0] : m_dn[0]), k1 = dy == 0 ? 0u : (dy < 0 ? m_up[1] : m_dn[1]);
-            const uint32_t k2 = dy == 0 ? 0u : (dy < 0 ? m_up[2] : m_dn[2]), k3 = dy == 0 ? 0u : (dy < 0 ? m_up[3] : m_dn[3]);
+            uint32_t km[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+              km[w] = (dy < 0 ? m_up[w] : (dy > 0 ? m_dn[w] : 0u)) | (kx == 0 ? m_lf[w] : (kx == 2 ? m_rt[w] : 0u));
+            const uint32_t k0 = km[0], k1 = km[1], k2 = km[2], k3 = km[3];
             for (int t = 0; t < c.T_acc; ++t) {
 #pragma unroll
               for (int sp = 0; sp < NSPLIT; ++sp) {
@@ -351,8 +358,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
       const int n0 = (tile % c.n_tiles) * c.N_TILE;
       const int64_t r = (int64_t)(tile / c.n_tiles) * kTileRows + q * 32 + lane;  // padded row (without guard)
       const int pp = (int)(r % p.P);
-      const int py = pp / p.Wp, px = pp - py * p.Wp;
-      const bool valid = (r < p.R_valid) && (px < p.W);
+      const int py = pp / p.W, px = pp - py * p.W;
+      const bool valid = r < p.R_valid;
       mbar_wait(acc_full(sc.stage), sc.phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc.stage * c.T_acc * c.N_TILE);
@@ -521,7 +528,7 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
   c->acc_stages = 512 / (c->T_acc * n_tile) >= 2 ? 2 : 1;
   c->acc_stages = env_int("SD_TC_ACC_STAGES", c->acc_stages) >= 2 && 512 / (c->T_acc * n_tile) >= 2 ? 2 : 1;
   const int c0 = d->C_in0, c1 = d->C_in - d->C_in0;
-  const int Wp = d->W_in + 1;
+  const int Wp = d->W_in;   // row stride of the dense pixel grid
   // Measured on B200 (profiles/r1_layer_sweep.txt): the pre-shifted (128-byte aligned) variant is SLOWER than plain
   // 16-byte-aligned tap starts (its 3x larger A stage forces KBLK = 16), so it is opt-in only.
   const int want_align = env_int("SD_TC_ALIGN", 0);
@@ -554,7 +561,7 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
   if (c->b_stages > kMaxBStages) c->b_stages = kMaxBStages;
   c->smem_bytes = 1024 + c->a_stages * c->a_stage_bytes + c->b_stages * c->b_stage_bytes;
   c->n_tiles = (d->C_out + n_tile - 1) / n_tile;
-  const int64_t R = (int64_t)d->B * d->H_in * (d->W_in + 1);
+  const int64_t R = (int64_t)d->B * d->H_in * d->W_in;
   c->m_tiles = (int)((R + kTileRows - 1) / kTileRows);
   c->c0_blocks = c0 / kblk;
   c->num_kblocks = c0 / kblk + c1 / kblk;

@@ -111,7 +111,15 @@ template <int kMaxPerLane>
 __global__ void __launch_bounds__(256) sample_step_kernel(const float* __restrict__ logits, int64_t* __restrict__ x_t,
                                                           uint8_t* __restrict__ unmasked, int64_t* __restrict__ x0_hat,
                                                           int64_t n_tokens, int K, float inv_t, float inv_temp,
-                                                          PhiloxCall cu, PhiloxCall ce, int64_t token_base) {
+                                                          PhiloxCall cu, PhiloxCall ce, int64_t token_base,
+                                                          const uint64_t* __restrict__ rng_dev) {
+  if (rng_dev != nullptr) {
+    // graph-replayable form: (seed, base offset) live in device memory; cu/ce carry offsets relative to the base
+    const uint64_t seed = rng_dev[0], base4 = rng_dev[1] >> 2;
+    cu.seed = ce.seed = seed;
+    cu.offset4 += base4;
+    ce.offset4 += base4;
+  }
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -254,9 +262,10 @@ int sd_philox_exponential(float* out, int64_t numel, uint64_t seed, uint64_t off
   return philox_fill(true, out, numel, seed, offset, index_base, numel_global, inc_out, stream);
 }
 
-int sd_sample_step(const float* logits, int64_t* x_t, uint8_t* unmasked, int64_t* x0_hat, int64_t n_tokens, int K,
-                   int t, float temp, uint64_t seed, uint64_t offset_uniform, uint64_t offset_exponential,
-                   int64_t token_base, int64_t n_tokens_global, void* stream) {
+static int sample_step_impl(const float* logits, int64_t* x_t, uint8_t* unmasked, int64_t* x0_hat, int64_t n_tokens,
+                            int K, int t, float temp, uint64_t seed, uint64_t offset_uniform,
+                            uint64_t offset_exponential, int64_t token_base, int64_t n_tokens_global,
+                            const uint64_t* rng_dev, void* stream) {
   SD_REQUIRE(n_tokens >= 0 && token_base >= 0 && n_tokens_global >= token_base + n_tokens, "sample_step: bad token range");
   SD_REQUIRE(K >= 32 && K % 128 == 0 && K <= 32 * kMaxPerLaneAll, "sample_step: K=%d must be a multiple of 128 in [128, %d]", K,
              32 * kMaxPerLaneAll);
@@ -277,7 +286,7 @@ int sd_sample_step(const float* logits, int64_t* x_t, uint8_t* unmasked, int64_t
   int64_t blocks = (n_tokens * 32 + 255) / 256;
 #define SD_SAMPLE_LAUNCH(PL)                                                                                  \
   sample_step_kernel<PL><<<grid_cap(blocks), 256, 0, as_stream(stream)>>>(logits, x_t, unmasked, x0_hat, n_tokens, K, \
-                                                                          inv_t, 1.0f / temp, cu, ce, token_base)
+                                                                          inv_t, 1.0f / temp, cu, ce, token_base, rng_dev)
   if (K <= 128) SD_SAMPLE_LAUNCH(4);
   else if (K <= 256) SD_SAMPLE_LAUNCH(8);
   else if (K <= 512) SD_SAMPLE_LAUNCH(16);
@@ -285,6 +294,21 @@ int sd_sample_step(const float* logits, int64_t* x_t, uint8_t* unmasked, int64_t
 #undef SD_SAMPLE_LAUNCH
   SD_LAUNCH_CHECK();
   return SD_OK;
+}
+
+int sd_sample_step(const float* logits, int64_t* x_t, uint8_t* unmasked, int64_t* x0_hat, int64_t n_tokens, int K,
+                   int t, float temp, uint64_t seed, uint64_t offset_uniform, uint64_t offset_exponential,
+                   int64_t token_base, int64_t n_tokens_global, void* stream) {
+  return sample_step_impl(logits, x_t, unmasked, x0_hat, n_tokens, K, t, temp, seed, offset_uniform,
+                          offset_exponential, token_base, n_tokens_global, nullptr, stream);
+}
+
+int sd_sample_step_dev(const float* logits, int64_t* x_t, uint8_t* unmasked, int64_t* x0_hat, int64_t n_tokens, int K,
+                       int t, float temp, const uint64_t* rng_dev, uint64_t rel_offset_uniform,
+                       uint64_t rel_offset_exponential, int64_t token_base, int64_t n_tokens_global, void* stream) {
+  SD_REQUIRE(rng_dev != nullptr, "sample_step_dev: rng_dev is null");
+  return sample_step_impl(logits, x_t, unmasked, x0_hat, n_tokens, K, t, temp, 0, rel_offset_uniform,
+                          rel_offset_exponential, token_base, n_tokens_global, rng_dev, stream);
 }
 
 int sd_denoiser_input(const int64_t* x_t, float* out, int B, int H, int W, int t, void* stream) {

@@ -283,26 +283,26 @@ class SamplerPlan:
     def offset_advance(self, sample_steps: int) -> int:
         return sample_steps * (self.inc_u + self.inc_e)
 
-    def _step(self, dp, lo, bi, t, temp, seed, off):
+    def _step(self, dp, lo, bi, t, temp, seed, off, rng_dev=None):
         hw = self.h * self.w
         xs = self.x_t[lo * hw:(lo + bi) * hw]
         us = self.unmasked[lo * hw:(lo + bi) * hw]
         logits = dp.run_tokens(xs, t)
-        check(lib().sd_sample_step(ptr(logits), ptr(xs), ptr(us), None, bi * hw, self.K, t, float(temp), int(seed), off,
-                                   off + self.inc_u, self.token_base + lo * hw, self.n_tokens_global, stream_ptr()))
+        if rng_dev is None:
+            check(lib().sd_sample_step(ptr(logits), ptr(xs), ptr(us), None, bi * hw, self.K, t, float(temp), int(seed),
+                                       off, off + self.inc_u, self.token_base + lo * hw, self.n_tokens_global,
+                                       stream_ptr()))
+        else:  # `off` is relative to the base offset stored in rng_dev
+            check(lib().sd_sample_step_dev(ptr(logits), ptr(xs), ptr(us), None, bi * hw, self.K, t, float(temp),
+                                           ptr(rng_dev), off, off + self.inc_u, self.token_base + lo * hw,
+                                           self.n_tokens_global, stream_ptr()))
 
-    def sample(self, temp: float, sample_steps: int, seed: int, offset0: int = 0,
-               x_init: Optional[torch.Tensor] = None, unmasked_init: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """x_init / unmasked_init (host or device, [b,1,h,w] or flat): start from a partially unmasked grid
-        instead of the all-mask grid of vq_diffusion.py:106-107; copied on the current stream (pinned host -> device)."""
-        if x_init is None:
+    def _enqueue(self, temp, sample_steps, seed, offset0, fill_x, fill_u, rng_dev=None):
+        """Enqueue the whole reverse-diffusion loop on the current stream (+ the sub-batch streams)."""
+        if fill_x:
             self.x_t.fill_(self.mask_id)
-        else:
-            self.x_t.copy_(x_init.reshape(-1), non_blocking=True)
-        if unmasked_init is None:
+        if fill_u:
             self.unmasked.zero_()
-        else:
-            self.unmasked.copy_(unmasked_init.reshape(-1), non_blocking=True)
         multi = len(self.subs) > 1
         if multi:
             cur = torch.cuda.current_stream()
@@ -315,15 +315,55 @@ class SamplerPlan:
             for (dp, lo, bi), s in zip(self.subs, self.streams):
                 if multi:
                     with torch.cuda.stream(s):
-                        self._step(dp, lo, bi, t, temp, seed, off)
+                        self._step(dp, lo, bi, t, temp, seed, off, rng_dev)
                 else:
-                    self._step(dp, lo, bi, t, temp, seed, off)
+                    self._step(dp, lo, bi, t, temp, seed, off, rng_dev)
             off += self.inc_u + self.inc_e
         if multi:
             for s in self.streams:
                 done = torch.cuda.Event()
                 done.record(s)
                 cur.wait_event(done)
+
+    def sample(self, temp: float, sample_steps: int, seed: int, offset0: int = 0,
+               x_init: Optional[torch.Tensor] = None, unmasked_init: Optional[torch.Tensor] = None,
+               use_graph: Optional[bool] = None) -> torch.Tensor:
+        """x_init / unmasked_init (host or device, [b,1,h,w] or flat): start from a partially unmasked grid
+        instead of the all-mask grid of vq_diffusion.py:106-107; copied on the current stream (pinned host -> device).
+
+        use_graph (default: env SD_SAMPLER_GRAPH, on): the loop (h*w steps x 8 kernels x sub-batches) is captured once
+        per (temp, steps) into a CUDA graph and replayed; the Philox (seed, offset) pair lives in device memory
+        (sd_sample_step_dev) so every replay draws a fresh, torch-identical stream."""
+        import os
+        import numpy as np
+        if use_graph is None:
+            use_graph = os.environ.get("SD_SAMPLER_GRAPH", "1") != "0"
+        if x_init is not None:
+            self.x_t.copy_(x_init.reshape(-1), non_blocking=True)
+        if unmasked_init is not None:
+            self.unmasked.copy_(unmasked_init.reshape(-1), non_blocking=True)
+        if not use_graph:
+            self._enqueue(temp, sample_steps, seed, offset0, x_init is None, unmasked_init is None)
+            return self.x_t.view(self.b, 1, self.h, self.w)
+        if not hasattr(self, "rng_dev"):
+            self.rng_dev = torch.zeros(2, dtype=torch.int64, device=self.x_t.device)
+            self._graphs = {}
+        state = np.array([int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset0)], dtype=np.uint64).view(np.int64)
+        self.rng_dev.copy_(torch.from_numpy(state))
+        key = (float(temp), int(sample_steps), x_init is None, unmasked_init is None)
+        g = self._graphs.get(key)
+        if g is None:
+            # one eager step first: lazy one-time initialisation (function attributes) must not happen under capture
+            xt_save, um_save = self.x_t.clone(), self.unmasked.clone()
+            self._enqueue(temp, 1, seed, 0, False, False, self.rng_dev)
+            self.x_t.copy_(xt_save)
+            self.unmasked.copy_(um_save)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue(temp, sample_steps, 0, 0, x_init is None, unmasked_init is None, self.rng_dev)
+            self._graphs[key] = g
+        g.replay()
         return self.x_t.view(self.b, 1, self.h, self.w)
 
 

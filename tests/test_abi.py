@@ -42,11 +42,11 @@ def test_struct_layout_matches_header():
 def test_geometry_queries_are_host_only():
     L = _lib.lib()
     assert L.sd_version() == 1
-    assert L.sd_stf_guard(7) == 16 and L.sd_stf_guard(28) == 32
-    # 256 images x 7 rows x (7+1 pad column) = 14336 rows = 112 tiles of 128, + 2 guards of 16
-    assert L.sd_stf_rows(256, 7, 7) == 14336 + 32
-    assert L.sd_stf_bytes(4, 256, 64, 7, 7) == 4 * 8 * (14336 + 32) * 8 * 2
-    assert L.sd_stf_bytes(1, 1, 3, 7, 7) == 1 * 1 * (128 + 32) * 8 * 2  # C rounded up to 8
+    assert L.sd_stf_guard(7) == 8 and L.sd_stf_guard(28) == 32
+    # 256 images x 49 pixels = 12544 rows = 98 tiles of 128 (dense: no padding is stored), + 2 guards of 8
+    assert L.sd_stf_rows(256, 7, 7) == 12544 + 16
+    assert L.sd_stf_bytes(4, 256, 64, 7, 7) == 4 * 8 * (12544 + 16) * 8 * 2
+    assert L.sd_stf_bytes(1, 1, 3, 7, 7) == 1 * 1 * (128 + 16) * 8 * 2  # C rounded up to 8, rows to 128
 
 
 def test_argument_errors_mirror_reference_exceptions():
