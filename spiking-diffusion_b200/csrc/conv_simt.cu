@@ -262,6 +262,189 @@ __global__ void __launch_bounds__(256) conv_real_const_lif_kernel(const SimtPara
   }
 }
 
+
+// Spike-input (STF) layers of the VQ-VAE that are not 3x3/stride-1 (enc.conv2 s2, enc.conv3 1x1, dec.convT1/2 s2,
+// dec.convT3 + memout + tanh).  One thread = one output pixel x 8 output channels x all T timesteps: the 8x8 weight
+// block of an (input chunk, tap) is a warp-uniform load held in registers and reused by the T timesteps (64*T FMAs per
+// 16 weight loads + T 16-byte spike loads).  For stride-2 transposed convolutions pixels are enumerated
+// phase-major (oy%2, ox%2 outermost) so that a warp shares one set of valid taps and does not diverge.
+template <int TMAX>
+__global__ void __launch_bounds__(128) conv_spike8_kernel(const SimtParams p) {
+  const sd_conv_desc& d = p.d;
+  const int T = d.T, Cout = d.C_out, Cin = d.C_in;
+  const int G8 = (Cout + 7) >> 3;
+  const int64_t npix = (int64_t)d.B * d.H_out * d.W_out;
+  const int64_t total = npix * G8;
+  const StfGeom gin(d.B, d.H_in, d.W_in);
+  const StfGeom gout(d.B, d.H_out, d.W_out);
+  const int Cin8_0 = c8(d.C_in0), Cin8_1 = c8(Cin - d.C_in0);
+  const int Cout8 = c8(Cout);
+  const bool phase_major = d.transposed && d.stride == 2 && (d.H_out % 2 == 0) && (d.W_out % 2 == 0);
+  const int Hh = d.H_out >> 1, Wh = d.W_out >> 1;
+  const float inv_tau = 1.0f / d.tau;
+  int tau_exp;
+  const bool fast = frexpf(d.tau, &tau_exp) == 0.5f && d.hard_reset && d.v_reset == 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int grp = (int)(i / npix);
+    int64_t pix = i - (int64_t)grp * npix;
+    int ox, oy, b;
+    if (phase_major) {
+      const int64_t per = (int64_t)d.B * Hh * Wh;
+      const int ph = (int)(pix / per);
+      int64_t q = pix - ph * per;
+      const int qx = (int)(q % Wh); q /= Wh;
+      const int qy = (int)(q % Hh);
+      b = (int)(q / Hh);
+      oy = qy * 2 + (ph >> 1);
+      ox = qx * 2 + (ph & 1);
+    } else {
+      ox = (int)(pix % d.W_out); pix /= d.W_out;
+      oy = (int)(pix % d.H_out);
+      b = (int)(pix / d.H_out);
+    }
+    const int co = grp << 3;
+    float acc[TMAX][8];
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+
+    for (int ky = 0; ky < d.kh; ++ky) {
+      int iy;
+      if (d.transposed) {
+        const int ny = oy + d.pad - ky;
+        if (ny < 0 || ny % d.stride) continue;
+        iy = ny / d.stride;
+      } else {
+        iy = oy * d.stride - d.pad + ky;
+      }
+      if (iy < 0 || iy >= d.H_in) continue;
+      for (int kx = 0; kx < d.kw; ++kx) {
+        int ix;
+        if (d.transposed) {
+          const int nx = ox + d.pad - kx;
+          if (nx < 0 || nx % d.stride) continue;
+          ix = nx / d.stride;
+        } else {
+          ix = ox * d.stride - d.pad + kx;
+        }
+        if (ix < 0 || ix >= d.W_in) continue;
+        const float* wt = p.w + (int64_t)(ky * d.kw + kx) * Cin * Cout + co;
+        const int64_t row = gin.row(b, iy, ix);
+        for (int cc = 0; cc < Cin; cc += 8) {
+          const bool seg1 = cc >= d.C_in0;
+          const __half* base = seg1 ? (const __half*)p.in2 : (const __half*)p.in;
+          const int C8s = seg1 ? Cin8_1 : Cin8_0;
+          const int cl = seg1 ? cc - d.C_in0 : cc;
+          float w[8][8];
+#pragma unroll
+          for (int ci = 0; ci < 8; ++ci) {
+            if (cc + ci < Cin) {
+              if ((Cout & 7) == 0) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(wt + (int64_t)(cc + ci) * Cout));
+                const float4 c = __ldg(reinterpret_cast<const float4*>(wt + (int64_t)(cc + ci) * Cout + 4));
+                w[ci][0] = a.x; w[ci][1] = a.y; w[ci][2] = a.z; w[ci][3] = a.w;
+                w[ci][4] = c.x; w[ci][5] = c.y; w[ci][6] = c.z; w[ci][7] = c.w;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[ci][j] = (co + j < Cout) ? __ldg(wt + (int64_t)(cc + ci) * Cout + j) : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) w[ci][j] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < TMAX; ++t) {
+            if (t < T) {
+              const uint4 raw = *reinterpret_cast<const uint4*>(base + gin.at(t, C8s, cl, row));
+              const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 f = __half22float2(h2[q]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  acc[t][j] = fmaf(f.x, w[2 * q][j], acc[t][j]);
+                  acc[t][j] = fmaf(f.y, w[2 * q + 1][j], acc[t][j]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = (co + j < Cout) ? p.scale[co + j] : 0.f;
+      sh[j] = (co + j < Cout) ? p.shift[co + j] : 0.f;
+    }
+    if (d.out_kind == SD_OUT_LIF) {
+      const int64_t orow = gout.row(b, oy, ox);
+      const int64_t vidx = ((int64_t)grp * gout.R_alloc + orow) * 8;
+      float v[8], cnt[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = p.v ? p.v[vidx + j] : (d.hard_reset ? d.v_reset : 0.f);
+        cnt[j] = 0.f;
+      }
+      __half* outp = (__half*)p.out;
+#pragma unroll
+      for (int t = 0; t < TMAX; ++t) {
+        if (t < T) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float x = fmaf(acc[t][j], sc[j], sh[j]);
+            float h;
+            bool s;
+            if (fast) {
+              h = fmaf(__fsub_rn(x, v[j]), inv_tau, v[j]);
+              s = h >= d.v_threshold;
+              v[j] = s ? 0.f : h;
+            } else {
+              const float dv = d.hard_reset ? __fsub_rn(x, __fsub_rn(v[j], d.v_reset)) : __fsub_rn(x, v[j]);
+              h = __fadd_rn(v[j], __fdiv_rn(dv, d.tau));
+              s = h >= d.v_threshold;
+              v[j] = d.hard_reset ? (s ? d.v_reset : h) : (s ? __fsub_rn(h, d.v_threshold) : h);
+            }
+            s = s && (co + j < Cout);
+            cnt[j] += s ? 1.f : 0.f;
+            const uint32_t bits = s ? 0x3C00u : 0u;
+            if (j & 1) pk[j >> 1] |= bits << 16; else pk[j >> 1] = bits;
+          }
+          *reinterpret_cast<uint4*>(outp + gout.at(t, Cout8, co, orow)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      if (p.v) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p.v[vidx + j] = v[j];
+      }
+      if (p.out_sum) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const __half2 h2 = __floats2half2_rn(cnt[j], cnt[j + 1]);
+          pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+        *reinterpret_cast<uint4*>(p.out_sum + gout.at(0, Cout8, co, orow)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    } else {  // SD_OUT_MEMOUT_TANH: sum_t coef[t] * (conv_t * scale + shift) -> tanh, fp32 [B, C_out, H_out, W_out]
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (co + j < Cout) {
+          float m = 0.f;
+#pragma unroll
+          for (int t = 0; t < TMAX; ++t)
+            if (t < T) m = __fadd_rn(m, __fmul_rn(fmaf(acc[t][j], sc[j], sh[j]), p.coef.c[t]));
+          ((float*)p.out)[(((int64_t)b * Cout + co + j) * d.H_out + oy) * d.W_out + ox] = tanhf(m);
+        }
+      }
+    }
+  }
+}
+
 // w (reference layout) -> [tap][ci][co]
 __global__ void pack_simt_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int kh,
                                  int kw, int transposed) {
@@ -356,6 +539,16 @@ int sd_conv_lif_simt(const sd_conv_desc* d, const sd_conv_args* a, void* stream)
     else if (d->T <= 8) conv_real_const_lif_kernel<8><<<(unsigned)bl, 256, 0, st>>>(p);
     else if (d->T <= 16) conv_real_const_lif_kernel<16><<<(unsigned)bl, 256, 0, st>>>(p);
     else conv_real_const_lif_kernel<32><<<(unsigned)bl, 256, 0, st>>>(p);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+  }
+  if (d->in_kind == SD_IN_STF && d->in_T == d->T && d->T <= 8 &&
+      (d->out_kind == SD_OUT_MEMOUT_TANH || (d->out_kind == SD_OUT_LIF && d->C_out % 8 == 0))) {
+    int64_t n8 = (int64_t)d->B * d->H_out * d->W_out * ((d->C_out + 7) / 8);
+    int64_t bl = (n8 + 127) / 128;
+    if (bl > cap * 2) bl = cap * 2;
+    if (d->T <= 4) conv_spike8_kernel<4><<<(unsigned)bl, 128, 0, st>>>(p);
+    else conv_spike8_kernel<8><<<(unsigned)bl, 128, 0, st>>>(p);
     SD_LAUNCH_CHECK();
     return SD_OK;
   }
