@@ -162,10 +162,13 @@ typedef struct sd_conv_args {
   void* out;             /* SD_OUT_LIF: STF spikes;  otherwise fp32 per out_kind */
   void* out_sum;         /* SD_OUT_LIF: optional STF [1][C_out/8][R][8] holding sum_t spikes, or NULL */
   const float* memout_coef_host; /* SD_OUT_MEMOUT_TANH: HOST pointer, T floats (the `memout.coef` buffer) */
+  void* workspace;       /* tc only: scratch of sd_conv_workspace_bytes(desc) bytes (0 for T <= 4), or NULL; used to
+                            carry the membrane potential between the T/4 passes when `v` is NULL */
 } sd_conv_args;
 
 int64_t sd_conv_weight_bytes_simt(const sd_conv_desc* d);
 int64_t sd_conv_weight_bytes_tc(const sd_conv_desc* d);
+int64_t sd_conv_workspace_bytes(const sd_conv_desc* d);
 /* w: the reference's own parameter layout, fp32 [C_out, C_in, kh, kw] (Conv2d) or [C_in, C_out, kh, kw]
  * (ConvTranspose2d).  tc packing splits each weight into nsplit fp16 terms after an exact power-of-two
  * per-output-channel scaling; chan_scale_out [C_out] receives the inverse scaling to be multiplied

@@ -24,7 +24,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 SYMBOLS = [
     "sd_last_error", "sd_version", "sd_device_info", "sd_stf_guard", "sd_stf_rows", "sd_stf_bytes",
     "sd_stf_from_nchw", "sd_stf_to_nchw", "sd_channel_affine", "sd_state_convert", "sd_lif_forward", "sd_memout", "sd_vq_feature", "sd_vq_lookup",
-    "sd_vq_gather", "sd_conv_weight_bytes_simt", "sd_conv_weight_bytes_tc", "sd_conv_pack_weights_simt",
+    "sd_vq_gather", "sd_conv_weight_bytes_simt", "sd_conv_weight_bytes_tc", "sd_conv_workspace_bytes", "sd_conv_pack_weights_simt",
     "sd_conv_pack_weights_tc", "sd_conv_lif_simt", "sd_conv_lif_tc", "sd_conv_tc_supported", "sd_philox_uniform",
     "sd_philox_exponential", "sd_philox_offset_increment", "sd_sample_step", "sd_sample_step_dev", "sd_denoiser_input", "sd_to_uint8",
 ]
@@ -87,7 +87,8 @@ class ConvArgs(ctypes.Structure):
     """struct sd_conv_args (include/sd_b200.h)."""
     _fields_ = [("in_", ctypes.c_void_p), ("in2", ctypes.c_void_p), ("weights", ctypes.c_void_p),
                 ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p), ("v", ctypes.c_void_p),
-                ("out", ctypes.c_void_p), ("out_sum", ctypes.c_void_p), ("memout_coef_host", ctypes.c_void_p)]
+                ("out", ctypes.c_void_p), ("out_sum", ctypes.c_void_p), ("memout_coef_host", ctypes.c_void_p),
+                ("workspace", ctypes.c_void_p)]
 
 
 IN_REAL_CONST, IN_REAL_SEQ, IN_STF = 0, 1, 2
@@ -118,6 +119,7 @@ def _declare(lib: ctypes.CDLL) -> None:
         "sd_vq_gather": (i, [vp, vp, vp, i, i, i, i, i, vp]),
         "sd_conv_weight_bytes_simt": (i64, [pd]),
         "sd_conv_weight_bytes_tc": (i64, [pd]),
+        "sd_conv_workspace_bytes": (i64, [pd]),
         "sd_conv_pack_weights_simt": (i, [pd, vp, vp, vp]),
         "sd_conv_pack_weights_tc": (i, [pd, vp, vp, vp, vp]),
         "sd_conv_lif_simt": (i, [pd, pa, vp]),

@@ -42,7 +42,10 @@ constexpr int kMaxBStages = 8;
 constexpr uint32_t kSmemBudget = 220 * 1024;
 
 struct TcConfig {
-  int T_acc;       // accumulators per tile (T for LIF, 1 for the T-summed linear read-out)
+  int T_acc;       // accumulators per pass (min(T, 4) timesteps for LIF, 1 for the T-summed linear read-out)
+  int n_tchunks;   // passes per tile: T / T_acc.  T = 8 / 16 run as 2 / 4 passes of 4 timesteps at N = 128 with the
+                   // membrane potential carried between passes in an L2-resident fp32 plane, instead of one pass at
+                   // N = 64 / 32 (whose A-operand fetch per MMA is amortised over too few columns)
   int N_TILE;
   int KBLK;        // input channels per K block
   int acc_stages;
@@ -64,7 +67,9 @@ struct TcParams {
   __half* out_spk;
   __half* out_sum;
   float* out_real;
-  float* v;
+  float* v;                 // state plane (caller's LIF state or workspace), or null
+  int v_load_initial;       // first pass starts from *v (else from v_reset)
+  int v_store_final;        // last pass writes v back
   int64_t R_alloc, G, R_valid;
   int C8_0, C8_1, Cout, Cout8;
   int T, H, W, Wp, P;
@@ -227,7 +232,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     const int ncopy = c.T_acc * chunks * c.ndx;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int64_t row0 = (int64_t)(tile / c.n_tiles) * kTileRows;
-      for (int kb = 0; kb < c.num_kblocks; ++kb) {
+      for (int kbi = 0; kbi < c.num_kblocks * c.n_tchunks; ++kbi) {
+        const int tch = kbi / c.num_kblocks, kb = kbi - tch * c.num_kblocks;
         if (lane == 0) {
           mbar_wait(a_empty(st.stage), st.phase ^ 1);
           mbar_expect_tx(a_full(st.stage), c.a_stage_bytes);
@@ -239,7 +245,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
         const int chunk0 = (seg1 ? kb - c.c0_blocks : kb) * chunks;
         for (int i = lane; i < ncopy; i += 32) {
           const int pl = i / c.ndx, dxi = i - pl * c.ndx;          // plane (t, chunk) and its dx copy
-          const int t = pl / chunks, ch = pl - t * chunks;
+          const int tl = pl / chunks, ch = pl - tl * chunks;
+          const int t = tch * c.T_acc + tl;
           const int dx = c.ndx == 3 ? dxi - 1 : 0;
           const __half* g = src + ((((int64_t)t * C8 + chunk0 + ch) * p.R_alloc) + p.G + row0 - c.halo + dx) * 8;
           bulk_g2s(a_base + st.stage * c.a_stage_bytes + (uint32_t)i * plane_bytes, g, plane_bytes, a_full(st.stage));
@@ -254,7 +261,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % c.n_tiles;
       const __half* wsrc = p.wpack + (int64_t)n_tile * c.num_kblocks * 9 * stage_halfs;
-      for (int it = 0; it < c.num_kblocks * 9; ++it) {
+      for (int itt = 0; itt < c.num_kblocks * 9 * c.n_tchunks; ++itt) {
+        const int it = itt % (c.num_kblocks * 9);      // every T pass streams the same weights again
         const int kb = it / 9, tap = tap_order(it - kb * 9);
         mbar_wait(b_empty(st.stage), st.phase ^ 1);
         if (elect_one()) {
@@ -278,7 +286,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     const uint32_t a_step_k = ((uint32_t)(2 * c.ndx) * plane_bytes) >> 4;
     const uint32_t b_step_sp = ((uint32_t)chunks * b_lbo) >> 4;
     const uint32_t b_step_k = (2u * b_lbo) >> 4;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    // one iteration per (tile, T pass)
+    for (int tile = blockIdx.x, tch = 0; tile < total_tiles;
+         (++tch == c.n_tchunks) ? (tch = 0, tile += gridDim.x) : 0) {
       mbar_wait(acc_empty(sc.stage), sc.phase ^ 1);
       tc_fence_after();
       const uint32_t d_base = tmem_base + (uint32_t)(sc.stage * c.T_acc * c.N_TILE);
@@ -354,9 +364,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     const bool tau_pow2 = frexpf(p.tau, &tau_exp) == 0.5f;
     const float inv_tau = 1.0f / p.tau;
     const bool fast_lif = tau_pow2 && p.hard_reset && p.v_reset == 0.f;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x, tch = 0; tile < total_tiles;
+         (++tch == c.n_tchunks) ? (tch = 0, tile += gridDim.x) : 0) {
+      const bool first_pass = tch == 0, last_pass = tch == c.n_tchunks - 1;
       const int n0 = (tile % c.n_tiles) * c.N_TILE;
-      const int64_t r = (int64_t)(tile / c.n_tiles) * kTileRows + q * 32 + lane;  // padded row (without guard)
+      const int64_t r = (int64_t)(tile / c.n_tiles) * kTileRows + q * 32 + lane;  // row (without guard)
       const int pp = (int)(r % p.P);
       const int py = pp / p.W, px = pp - py * p.W;
       const bool valid = r < p.R_valid;
@@ -377,7 +389,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
         if (p.out_kind == SD_OUT_LIF) {
           float v[16], cnt[16];
           const int64_t vrow = ((int64_t)(n >> 3) * p.R_alloc + p.G + r) * 8;  // chunk n/8; next chunk + R_alloc*8
-          if (p.v != nullptr && valid && n < p.Cout) {
+          if (p.v != nullptr && valid && n < p.Cout && (!first_pass || p.v_load_initial)) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const float4 a = *reinterpret_cast<const float4*>(p.v + vrow + (int64_t)h * p.R_alloc * 8);
@@ -391,9 +403,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) cnt[j] = 0.f;
-          for (int t = 0; t < c.T_acc; ++t) {
+          if (!first_pass && p.out_sum != nullptr && valid) {   // spike counts of the earlier passes
+            const __half* o = p.out_sum + ((int64_t)(n >> 3) * p.R_alloc + p.G + r) * 8;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint4 raw = *reinterpret_cast<const uint4*>(o + (int64_t)h * p.R_alloc * 8);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(h2[k]);
+                cnt[8 * h + 2 * k] = f.x; cnt[8 * h + 2 * k + 1] = f.y;
+              }
+            }
+          }
+          for (int tl = 0; tl < c.T_acc; ++tl) {
+            const int t = tch * c.T_acc + tl;
             uint32_t acc[16];
-            tc_ld16(t_base + (uint32_t)(t * c.N_TILE + cc), acc);
+            tc_ld16(t_base + (uint32_t)(tl * c.N_TILE + cc), acc);
             tc_ld_wait();
             uint32_t packed[8];
             if (fast_lif) {
@@ -439,7 +465,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
               *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               *reinterpret_cast<uint4*>(o + p.R_alloc * 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
-            if (p.v != nullptr) {
+            if (p.v != nullptr && (!last_pass || p.v_store_final)) {
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 float* o = p.v + vrow + (int64_t)h * p.R_alloc * 8;
@@ -512,6 +538,8 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
   const char* why;
   if (!tc_supported(d, &why)) { set_error("conv_tc: unsupported descriptor: %s", why); return SD_ERR_UNSUPPORTED; }
   c->T_acc = d->out_kind == SD_OUT_LIF ? d->T : 1;
+  if (d->out_kind == SD_OUT_LIF && d->T > 4 && d->T % 4 == 0 && env_int("SD_TC_TCHUNK", 1)) c->T_acc = 4;
+  c->n_tchunks = d->out_kind == SD_OUT_LIF ? d->T / c->T_acc : 1;
   int n_tile;
   // Larger N amortises the A-operand fetch from shared memory (4 KB per MMA whatever N is): measured on B200,
   // N = 128 without epilogue overlap beats N = 64 with two TMEM stages (profiles/).
@@ -632,6 +660,14 @@ int sd_conv_tc_supported(const sd_conv_desc* d) {
   return tc_config(d, &c) == SD_OK ? 1 : 0;
 }
 
+int64_t sd_conv_workspace_bytes(const sd_conv_desc* d) {
+  TcConfig c;
+  if (!d || validate_conv_desc(d) != SD_OK || tc_config(d, &c) != SD_OK) return 0;
+  if (c.n_tchunks <= 1) return 0;
+  // one fp32 state plane [C_out/8][R_alloc][8]
+  return (int64_t)c8(d->C_out) * stf_rows(d->B, d->H_out, d->W_out) * 8 * (int64_t)sizeof(float);
+}
+
 int64_t sd_conv_weight_bytes_tc(const sd_conv_desc* d) {
   TcConfig c;
   if (!d || validate_conv_desc(d) != SD_OK || tc_config(d, &c) != SD_OK) return 0;
@@ -677,7 +713,14 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
   p.wpack = (const __half*)a->weights;
   p.scale = a->scale;
   p.shift = a->shift;
-  p.v = a->v;
+  p.v = a->v ? a->v : (float*)a->workspace;
+  p.v_load_initial = a->v != nullptr;
+  p.v_store_final = a->v != nullptr;
+  if (c.n_tchunks > 1 && p.v == nullptr) {
+    set_error("conv_tc: T=%d runs as %d passes and needs args.v or args.workspace (sd_conv_workspace_bytes)", d->T,
+              c.n_tchunks);
+    return SD_ERR_INVALID;
+  }
   if (d->out_kind == SD_OUT_LIF) { p.out_spk = (__half*)a->out; p.out_sum = (__half*)a->out_sum; }
   else p.out_real = (float*)a->out;
   StfGeom g(d->B, d->H_in, d->W_in);

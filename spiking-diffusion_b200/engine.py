@@ -117,6 +117,8 @@ class FusedLayer:
         self.impl = impl
         self._fn = L.sd_conv_lif_tc if impl == "tc" else L.sd_conv_lif_simt
         self._coef = None
+        ws = L.sd_conv_workspace_bytes(ctypes.byref(d)) if impl == "tc" else 0
+        self._ws = torch.empty(ws, dtype=torch.uint8, device=self.device) if ws else None
         if share is not None and share.impl == impl and share.desc.nsplit == nsplit and share.T == T:
             # packed weights do not depend on the batch size: sub-batch plans reuse them
             self.wpack, self.scale, self.shift, self._coef = share.wpack, share.scale, share.shift, share._coef
@@ -175,6 +177,7 @@ class FusedLayer:
         a.scale, a.shift, a.v = ptr(self.scale), ptr(self.shift), ptr(v)
         a.out, a.out_sum = ptr(out), ptr(out_sum)
         a.memout_coef_host = ctypes.cast(self._coef, ctypes.c_void_p) if self._coef is not None else None
+        a.workspace = ptr(self._ws)
         check(self._fn(ctypes.byref(self.desc), ctypes.byref(a), stream_ptr()))
         return out
 

@@ -20,6 +20,41 @@ from .._lib import check, lib, ptr, stream_ptr
 from ..activation_based import functional, layer, neuron, surrogate
 
 
+def get_data_for_diff(train_loader, model, T: int = None):
+    """Encode a dataset into code-index grids for diffusion training (mirrors vq_diffusion.py:23-36).
+
+    Like the reference, the model is put in eval mode and is NOT reset between batches, so LIF membrane state leaks
+    from one batch into the next; call ``functional.reset_net(model)`` per batch
+    yourself if that is not wanted.  ``T`` defaults to the model's timestep count (the reference hard-codes 16)."""
+    print('prepare data for train diffusion...')
+    model.eval()
+    T = getattr(model, "T", 16) if T is None else T
+    train_indices = []
+    for images, labels in train_loader:
+        images = images - 0.5  # normalize to [-0.5, 0.5]
+        images = images.cuda()
+        images_spike = images.unsqueeze(0).repeat(T, 1, 1, 1, 1)
+        with torch.inference_mode():
+            _, _, encoding_indices = model(images_spike, images)
+            h, w = images.shape[-2] // 4, images.shape[-1] // 4
+            train_indices.append(encoding_indices.reshape(images.shape[0], h, w).cpu())
+    return train_indices
+
+
+def load_reference_state_dict(module, state_dict, strict: bool = True):
+    """Load a reference checkpoint (R/main.py:199,286 ``torch.save(model.state_dict())``) into a module built with a
+    different ``T``: the ``*.memout.coef`` buffers are T-bound ((16,1,1,1,1) in reference checkpoints, SURVEY.md
+    finding 1) and are recomputed for this module's T instead of being copied."""
+    own = module.state_dict()
+    fixed = {}
+    for k, v in state_dict.items():
+        if k.endswith("memout.coef") and k in own and own[k].shape != v.shape:
+            fixed[k] = own[k]
+        else:
+            fixed[k] = v
+    return module.load_state_dict(fixed, strict=strict)
+
+
 class DummyModel(nn.Module):
     """6-layer spiking conv denoiser with one skip connection (vq_diffusion.py:150-208)."""
 

@@ -34,9 +34,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    # 17 ints + 3 floats + 2 ints, no padding; 9 pointers
+    # 17 ints + 3 floats + 2 ints, no padding; 10 pointers
     assert ctypes.sizeof(_lib.ConvDesc) == 22 * 4
-    assert ctypes.sizeof(_lib.ConvArgs) == 9 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_lib.ConvArgs) == 10 * ctypes.sizeof(ctypes.c_void_p)
 
 
 def test_geometry_queries_are_host_only():
