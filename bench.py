@@ -220,31 +220,56 @@ def run_ours(args, wl, rank, world, local_rank):
     clk = clocks.stop()
     e2e = n_global * args.steps / float(e2e_s)
 
-    # ---- roofline of the dominant kernel: one instrumented denoiser pass --------------------------------------
+    # ---- roofline of the dominant kernel --------------------------------------------------------------------------
+    # The timed region launches every layer once per sub-batch, the sub-batches on separate streams.  Each layer is
+    # therefore measured as it runs there: one "launch group" = the layer's launches of all sub-batches, forked onto
+    # their streams from one start event and joined into one stop event.  FLOPs are those of the whole group.
     roof = None
     if rank == 0:
-        dp = splan.dp
-        layers = [("den.conv2", dp.l2, dp.x1, dp.x2, None), ("den.conv3", dp.l3, dp.x2, dp.x3, None),
-                  ("den.conv4", dp.l4, dp.x3, dp.x4, None), ("den.conv5", dp.l5, dp.x4, dp.x5, dp.x5s)]
-        acc = {n: [] for n, *_ in layers}
-        for rep in range(12):
+        names = [("den.conv2", "l2", "x1", "x2", None), ("den.conv3", "l3", "x2", "x3", None),
+                 ("den.conv4", "l4", "x3", "x4", None), ("den.conv5", "l5", "x4", "x5", "x5s")]
+        cur = torch.cuda.current_stream()
+        acc = {n: [] for n, *_ in names}
+        for rep in range(14):
             flush.zero_()
-            for n, l, xi, xo, xs in layers:
+            for n, ln, xi, xo, xs in names:
                 a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); l.run(xi, xo, out_sum=xs); c.record()
+                a.record(cur)
+                for (dp, _, _), st in zip(splan.subs, splan.streams):
+                    run = lambda: getattr(dp, ln).run(getattr(dp, xi), getattr(dp, xo), out_sum=getattr(dp, xs) if xs else None)
+                    if st is None:
+                        run()
+                    else:
+                        st.wait_event(a)
+                        with torch.cuda.stream(st):
+                            run()
+                        done = torch.cuda.Event()
+                        done.record(st)
+                        cur.wait_event(done)
+                c.record(cur)
                 acc[n].append((a, c))
         torch.cuda.synchronize()
         pk = peaks()
         per = {}
-        for n, l, *_ in layers:
-            t = sorted(a.elapsed_time(c) for a, c in acc[n][2:])
+        for n, ln, *_ in names:
+            t = sorted(a.elapsed_time(c) for a, c in acc[n][3:])
             mean_ms = sum(t) / len(t)
-            per[n] = dict(ms=round(mean_ms, 4), tflops=round(l.flops() / mean_ms / 1e9, 1), impl=l.impl)
+            fl = sum(getattr(dp, ln).flops() for dp, _, _ in splan.subs)
+            per[n] = dict(ms=round(mean_ms, 4), tflops=round(fl / mean_ms / 1e9, 1), impl=getattr(splan.dp, ln).impl,
+                          launches_per_group=len(splan.subs))
         dom = max(per, key=lambda k: per[k]["ms"])
+        traffic = None
+        tf = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tf):
+            traffic = json.load(open(tf)).get(f"{args.workload}:{dom}:streams{len(splan.subs)}")
+        step_flops = splan.flops_per_image(steps_diff) * b + vplan.flops()
         roof = {"bound": "tensor", "kernel": f"conv3x3_tc_kernel ({dom})", "achieved": per[dom]["tflops"],
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(per[dom]["tflops"] / pk["tf_sustained"], 4),
-                "traffic": None, "peak_source": pk["source"] + " bf16_tflops_sustained", "nsplit": args.nsplit,
-                "flops_definition": "dense un-split 2*MAC*B*T (SURVEY.md 8(d)); weight-split passes are overhead",
+                "traffic": traffic, "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                "nsplit": args.nsplit,
+                "flops_definition": "dense un-split 2*MAC*B*T (SURVEY.md 8(d)); the two exact fp16 weight terms are overhead, "
+                                    "so the ceiling of this fraction is 0.5",
+                "whole_step_tflops": round(step_flops * n_global / b / (total_ms / args.steps) / 1e9, 1) if world == 1 else None,
                 "layers": per}
 
     if rank != 0:

@@ -539,16 +539,21 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
   if (!tc_supported(d, &why)) { set_error("conv_tc: unsupported descriptor: %s", why); return SD_ERR_UNSUPPORTED; }
   c->T_acc = d->out_kind == SD_OUT_LIF ? d->T : 1;
   if (d->out_kind == SD_OUT_LIF && d->T > 4 && d->T % 4 == 0 && env_int("SD_TC_TCHUNK", 1)) c->T_acc = 4;
+  if (d->out_kind == SD_OUT_LIF) {
+    const int tacc = env_int("SD_TC_TACC", 0);           // experiment knob: timesteps per pass
+    if (tacc > 0 && tacc <= d->T && d->T % tacc == 0) c->T_acc = tacc;
+  }
   c->n_tchunks = d->out_kind == SD_OUT_LIF ? d->T / c->T_acc : 1;
   int n_tile;
   // Larger N amortises the A-operand fetch from shared memory (4 KB per MMA whatever N is): measured on B200,
   // N = 128 without epilogue overlap beats N = 64 with two TMEM stages (profiles/).
-  if (c->T_acc * 128 <= 512) n_tile = 128;
+  if (c->T_acc * 256 <= 512 && d->C_out >= 256 && env_int("SD_TC_N256", 0)) n_tile = 256;
+  else if (c->T_acc * 128 <= 512) n_tile = 128;
   else if (c->T_acc * 64 <= 512) n_tile = 64;
   else n_tile = 32;
   n_tile = env_int("SD_TC_NTILE", n_tile);
   while (n_tile > 32 && n_tile / 2 >= d->C_out) n_tile /= 2;
-  if (!(n_tile == 32 || n_tile == 64 || n_tile == 128) || c->T_acc * n_tile > 512) {
+  if (!(n_tile == 32 || n_tile == 64 || n_tile == 128 || n_tile == 256) || c->T_acc * n_tile > 512) {
     set_error("conv_tc: bad N tile %d for T=%d", n_tile, c->T_acc);
     return SD_ERR_UNSUPPORTED;
   }
@@ -569,7 +574,7 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
     static const int kblks[3] = {64, 32, 16};
     for (int i = 0; i < 3 && !found; ++i) {
       const int kblk = kblks[i];
-      if (kblk_pref ? kblk != kblk_pref : (ndx == 1 && kblk == 64)) continue;   // default: 32 (then 16)
+      if (kblk_pref && kblk != kblk_pref) continue;   // default: the largest K block that leaves >= 2 A + 4 B stages
       if (c0 % kblk || c1 % kblk) continue;
       c->a_stage_bytes = (uint32_t)c->T_acc * (kblk / 8) * ndx * c->rows_ld * 16;
       c->b_stage_bytes = (uint32_t)d->nsplit * (kblk / 8) * n_tile * 16;

@@ -12,11 +12,11 @@ import bench  # noqa: E402
 from spiking_diffusion_b200 import engine  # noqa: E402
 
 CONFIGS = [
-    {"SD_TC_ALIGN": "1"},
-    {"SD_TC_ALIGN": "0"},
-    {"SD_TC_ALIGN": "0", "SD_TC_KBLK": "64"},
-    {"SD_TC_ALIGN": "1", "SD_TC_NTILE": "64"},
-    {"SD_TC_ALIGN": "0", "SD_TC_NTILE": "64", "SD_TC_KBLK": "64"},
+    {},
+    {"SD_TC_TACC": "2"},
+    {"SD_TC_TACC": "2", "SD_TC_N256": "1"},
+    {"SD_TC_TACC": "1", "SD_TC_N256": "1"},
+    {"SD_TC_TACC": "2", "SD_TC_KBLK": "64"},
 ]
 
 

@@ -74,7 +74,7 @@ def summarize_launches(csvf, out, title):
             f.write(f"{k:44s} {len(v):8d} {sum(v):11.1f} {sum(v) / len(v):9.2f} {100 * sum(v) / tot:6.1f}%\n")
         f.write(f"{'TOTAL':44s} {sum(len(v) for v in agg.values()):8d} {tot:11.1f}\n\n# one diffusion step, in launch order:\n")
         start = next((i for i, s in enumerate(seq) if s[0].startswith("denoiser_input")), 0)
-        for name, grid, v in seq[start:start + 8]:
+        for name, grid, v in seq[start:start + 16]:
             f.write(f"  {name:44s} grid {grid:14s} {v:9.2f} us\n")
     print("wrote", out)
 
@@ -84,8 +84,8 @@ if __name__ == "__main__":
     os.makedirs(PROF, exist_ok=True)
     if os.path.exists(os.path.join(OUT, "p_launches.csv")):
         summarize_launches(os.path.join(OUT, "p_launches.csv"), os.path.join(PROF, f"{tag}_launch_list.txt"),
-                           "bench.py --steps 1 --warmup 1 (cfg2: b=256, T=4, K=128, 49 steps + decode), 1 sampler stream, no graph")
-    for rep, name, title in (("p_conv_tc.ncu-rep", "conv3x3_tc", "fused conv+BN+LIF tcgen05 kernel: den.conv3, den.conv4, den.conv5 of one diffusion step (cfg2)"),
+                           "bench.py --steps 1 --warmup 1 (cfg2: b=256, T=4, K=128, 49 steps + decode), 2 sampler streams (2 x 128 images), SD_SAMPLER_GRAPH=0")
+    for rep, name, title in (("p_conv_tc.ncu-rep", "conv3x3_tc", "fused conv+BN+LIF tcgen05 kernel: den.conv2..conv6 of one diffusion step of one 128-image sub-batch (cfg2, 2 sampler streams)"),
                              ("p_sample.ncu-rep", "sample_step", "fused sampling-step kernel (cfg2: 12544 tokens, K=128)"),
                              ("p_conv1.ncu-rep", "conv_real_const_lif", "den.conv1: real-input conv + BN + LIF (cfg2)")):
         if os.path.exists(os.path.join(OUT, rep)):
