@@ -84,6 +84,14 @@ int sd_lif_forward(const float* x_seq, float* v, float* spike_seq, float* h_seq_
                    int T, int64_t N, float tau, float v_threshold, float v_reset,
                    int hard_reset, int decay_input, void* stream);
 
+/* (a2 / f.1) surrogate-gradient BPTT of the same recurrence, ATan surrogate with slope `alpha`
+ * (SJ/activation_based/neuron.py:210-258, surrogate.py:663-678; the reference's generated kernel is reproduced in
+ * SURVEY.md Appendix A).  h_seq is the pre-fire potential saved by sd_lif_forward.  grad_v_last (optional, [N]) is
+ * dL/dv after the last step; grad_v_init (optional, [N]) receives dL/dv before the first step. */
+int sd_lif_backward(const float* grad_spike_seq, const float* grad_v_last_or_null, const float* h_seq,
+                    float* grad_x_seq, float* grad_v_init_or_null, int T, int64_t N, float tau, float v_threshold,
+                    float v_reset, int hard_reset, int decay_input, int detach_reset, float alpha, void* stream);
+
 /* ---- (a6) MembraneOutputLayer -----------------------------------------------------------------
  * Replaces R/snn_model/snn_layers.py:28-41 (coef[t] = 0.8^(T-1-t), any T).
  * x: fp32 [T, N] -> out fp32 [N]; apply_tanh != 0 fuses the torch.tanh of R/snn_model/vae_model.py:186.

@@ -77,6 +77,46 @@ def lif_multi_step(x_seq: Tensor, v: Optional[Tensor] = None, tau: float = 2.0, 
     return spike_seq, v
 
 
+class _ATanSpike(torch.autograd.Function):
+    """Heaviside forward, ATan surrogate backward: SJ/activation_based/surrogate.py:663-678."""
+
+    @staticmethod
+    def forward(ctx, x, alpha):
+        ctx.save_for_backward(x)
+        ctx.alpha = alpha
+        return (x >= 0).to(x)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, = ctx.saved_tensors
+        return ctx.alpha / 2 / (1 + (math.pi / 2 * ctx.alpha * x).pow(2)) * grad_output, None
+
+
+def lif_multi_step_train(x_seq: Tensor, v: Optional[Tensor] = None, tau: float = 2.0, v_threshold: float = 1.0,
+                         v_reset: Optional[float] = 0.0, decay_input: bool = True, detach_reset: bool = False,
+                         alpha: float = 2.0):
+    """Differentiable training branch: BaseNode.multi_step_forward -> single_step_forward
+    (SJ/activation_based/neuron.py:244-258,210-242), neuronal_charge (:726-743), neuronal_fire (:161-177),
+    neuronal_reset (:179-205).  Returns (spike_seq, v_last); gradients flow through the ATan surrogate."""
+    if v is None:
+        v = torch.full_like(x_seq[0], 0.0 if v_reset is None else float(v_reset))
+    out = []
+    for t in range(x_seq.shape[0]):
+        x = x_seq[t]
+        if decay_input:
+            v = v + (x - v) / tau if (v_reset is None or v_reset == 0.0) else v + (x - (v - v_reset)) / tau
+        else:
+            v = v * (1.0 - 1.0 / tau) + x if (v_reset is None or v_reset == 0.0) else v - (v - v_reset) / tau + x
+        spike = _ATanSpike.apply(v - v_threshold, alpha)
+        spike_d = spike.detach() if detach_reset else spike
+        if v_reset is None:
+            v = v - spike_d * v_threshold
+        else:
+            v = (1.0 - spike_d) * v + spike_d * v_reset
+        out.append(spike)
+    return torch.stack(out), v
+
+
 # --------------------------------------------------------------------------------------------------
 # Read-out layers
 # --------------------------------------------------------------------------------------------------

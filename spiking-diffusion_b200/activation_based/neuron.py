@@ -16,6 +16,39 @@ from .._lib import check, lib, ptr, stream_ptr
 from . import base, surrogate
 
 
+class _LIFFunction(torch.autograd.Function):
+    """Multi-step LIF with surrogate-gradient BPTT: forward = sd_lif_forward (saving the pre-fire potential),
+    backward = sd_lif_backward.  Inputs: x_seq [T, ...], v_init [...]; outputs: spike_seq, v_last."""
+
+    @staticmethod
+    def forward(ctx, x_seq, v_init, tau, v_th, v_reset, decay_input, detach_reset, alpha):
+        x_seq = x_seq.contiguous()
+        v = v_init.contiguous().clone()
+        spikes = torch.empty_like(x_seq)
+        h_seq = torch.empty_like(x_seq)
+        T, N = x_seq.shape[0], x_seq[0].numel()
+        check(lib().sd_lif_forward(ptr(x_seq), ptr(v), ptr(spikes), ptr(h_seq), T, N, float(tau), float(v_th),
+                                   0.0 if v_reset is None else float(v_reset), int(v_reset is not None), int(decay_input),
+                                   stream_ptr()))
+        ctx.save_for_backward(h_seq)
+        ctx.cfg = (float(tau), float(v_th), v_reset, bool(decay_input), bool(detach_reset), float(alpha))
+        return spikes, v
+
+    @staticmethod
+    def backward(ctx, grad_spikes, grad_v_last):
+        h_seq, = ctx.saved_tensors
+        tau, v_th, v_reset, decay_input, detach_reset, alpha = ctx.cfg
+        T, N = h_seq.shape[0], h_seq[0].numel()
+        gs = grad_spikes.contiguous().float() if grad_spikes is not None else torch.zeros_like(h_seq)
+        gv = grad_v_last.contiguous().float() if grad_v_last is not None else None
+        grad_x = torch.empty_like(h_seq)
+        grad_v0 = torch.empty_like(h_seq[0])
+        check(lib().sd_lif_backward(ptr(gs), ptr(gv), ptr(h_seq), ptr(grad_x), ptr(grad_v0), T, N, tau, v_th,
+                                    0.0 if v_reset is None else float(v_reset), int(v_reset is not None), int(decay_input),
+                                    int(detach_reset), alpha, stream_ptr()))
+        return grad_x, grad_v0, None, None, None, None, None, None
+
+
 class BaseNode(base.MemoryModule):
     def __init__(self, v_threshold: float = 1.0, v_reset: Optional[float] = 0.0,
                  surrogate_function: Callable = surrogate.Sigmoid(), detach_reset: bool = False, step_mode="s",
@@ -75,8 +108,6 @@ class LIFNode(BaseNode):
     def _run(self, x_seq: torch.Tensor) -> torch.Tensor:
         if not x_seq.is_cuda:
             raise RuntimeError("LIFNode.forward needs a CUDA tensor: spiking_diffusion_b200 has no CPU path")
-        if self.training and x_seq.requires_grad:
-            raise NotImplementedError("surrogate-gradient BPTT is not implemented in this round (SURVEY.md 8(f) rank 1)")
         if x_seq.dtype != torch.float32:
             raise NotImplementedError(f"LIFNode kernel is fp32 only, got {x_seq.dtype}")
         if x_seq.shape[0] == 0:
@@ -86,6 +117,17 @@ class LIFNode(BaseNode):
         if self.v.shape != x_seq.shape[1:]:
             raise ValueError(f"membrane state shape {tuple(self.v.shape)} does not match input {tuple(x_seq.shape[1:])}; "
                              "call reset() between inputs of different shape")
+        if self.training and torch.is_grad_enabled() and (x_seq.requires_grad or self.v.requires_grad):
+            # training branch (neuron.py:244-258): same spikes as the eval kernel, gradients by surrogate BPTT
+            sf = self.surrogate_function
+            if not isinstance(sf, surrogate.ATan) or not getattr(sf, "spiking", True):
+                raise NotImplementedError("surrogate-gradient BPTT is implemented for the spiking ATan surrogate only")
+            spikes, v = _LIFFunction.apply(x_seq, self.v, self.tau, self.v_threshold, self.v_reset, self.decay_input,
+                                           self.detach_reset, sf.alpha)
+            self.v = v
+            if self.store_v_seq:
+                raise NotImplementedError("store_v_seq is not available on the autograd path")
+            return spikes
         v = self.v.contiguous()
         spikes = torch.empty_like(x_seq)
         h_seq = torch.empty_like(x_seq) if self.store_v_seq else None

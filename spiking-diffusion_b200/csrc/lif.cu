@@ -173,6 +173,42 @@ static int launch_lif(const float* x, float* v, float* spk, float* h, int T, int
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Surrogate-gradient BPTT of the LIF recurrence (training branch: SJ/activation_based/neuron.py:210-258 with the
+// ATan surrogate, surrogate.py:663-678).  Same reverse-time recurrence as the reference's generated kernel
+// (SURVEY.md Appendix A): one thread per neuron walks t = T-1 .. 0 carrying dL/dh.  HBM-bound: 12 B per
+// neuron-timestep (grad_spike in, h in, grad_x out).
+struct LifBwdParams {
+  float inv_tau, v_th, v_reset, alpha;
+  int hard_reset, decay_input, detach_reset;
+};
+
+__global__ void __launch_bounds__(256) lif_backward_kernel(const float* __restrict__ grad_spike,
+                                                           const float* __restrict__ grad_v_last,
+                                                           const float* __restrict__ h_seq, float* __restrict__ grad_x,
+                                                           float* __restrict__ grad_v_init, int T, int64_t N,
+                                                           LifBwdParams p) {
+  const float keep = 1.0f - p.inv_tau;          // d h[t+1] / d v[t]
+  const float half_pi_alpha = 1.57079632679489661923f * p.alpha;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    float grad_v = grad_v_last ? grad_v_last[i] : 0.f;   // dL/dv[T-1] from outside (the stored state)
+    for (int t = T - 1; t >= 0; --t) {
+      const float h = h_seq[(int64_t)t * N + i];
+      const float over = h - p.v_th;
+      const float s = over >= 0.f ? 1.f : 0.f;
+      const float ax = half_pi_alpha * over;
+      const float g = p.alpha / 2.0f / (1.0f + ax * ax);          // d s / d h   (surrogate.py:663-665)
+      float dv_dh;                                                 // d v[t] / d h[t]
+      if (p.hard_reset) dv_dh = p.detach_reset ? (1.f - s) : (1.f - s) + (p.v_reset - h) * g;
+      else              dv_dh = p.detach_reset ? 1.f : 1.f - p.v_th * g;
+      const float grad_h = grad_v * dv_dh + grad_spike[(int64_t)t * N + i] * g;
+      grad_x[(int64_t)t * N + i] = p.decay_input ? grad_h * p.inv_tau : grad_h;
+      grad_v = grad_h * keep;                                      // flows to v[t-1]
+    }
+    if (grad_v_init) grad_v_init[i] = grad_v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 __global__ void memout_kernel(const float* __restrict__ x, float* __restrict__ out, int T, int64_t N,
                               MemoutCoef coef, int apply_tanh) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
@@ -299,6 +335,21 @@ int sd_lif_forward(const float* x_seq, float* v, float* spike_seq, float* h_seq,
     if (decay_input) { SD_LIF_DISPATCH(false, true); } else { SD_LIF_DISPATCH(false, false); }
   }
 #undef SD_LIF_DISPATCH
+}
+
+int sd_lif_backward(const float* grad_spike_seq, const float* grad_v_last, const float* h_seq, float* grad_x_seq,
+                    float* grad_v_init, int T, int64_t N, float tau, float v_threshold, float v_reset, int hard_reset,
+                    int decay_input, int detach_reset, float alpha, void* stream) {
+  SD_REQUIRE(tau > 1.0f, "LIFNode requires tau > 1, got %f", (double)tau);
+  SD_REQUIRE(T >= 0 && N >= 0, "negative size");
+  if (T == 0 || N == 0) return SD_OK;
+  SD_REQUIRE(grad_spike_seq && h_seq && grad_x_seq, "null pointer argument");
+  SD_DEVICE_OR_RETURN();
+  LifBwdParams p{1.0f / tau, v_threshold, v_reset, alpha, hard_reset, decay_input, detach_reset};
+  lif_backward_kernel<<<grid_for(N), 256, 0, as_stream(stream)>>>(grad_spike_seq, grad_v_last, h_seq, grad_x_seq,
+                                                                  grad_v_init, T, N, p);
+  SD_LAUNCH_CHECK();
+  return SD_OK;
 }
 
 int sd_memout(const float* x, float* out, const float* coef_host, int T, int64_t N, int apply_tanh, void* stream) {

@@ -94,3 +94,27 @@ def test_memout_matches_oracle(T):
     assert float((m(x.cuda(), apply_tanh=True).cpu() - torch.tanh(ref)).abs().max()) <= 1e-6
     with pytest.raises(RuntimeError):
         MembraneOutputLayer(16).cuda()(torch.zeros(4, 1, 1, 2, 2).cuda())   # SURVEY.md finding 1: T-bound coef
+
+
+@pytest.mark.parametrize("vr,detach,decay", [(0.0, False, True), (None, False, True), (-0.5, True, True), (0.0, False, False),
+                                             (None, True, False)])
+def test_surrogate_gradient_bptt_matches_oracle(vr, detach, decay):
+    """(a2 / f.1) training branch: spikes identical to the eval kernel, gradients by surrogate BPTT (ATan, alpha=2)
+    vs torch autograd through the oracle's restatement.  Tolerance: fp32, rtol 1e-5."""
+    from spiking_diffusion_b200.activation_based import surrogate
+    g = torch.Generator().manual_seed(9)
+    x_cpu = (torch.rand(6, 3, 16, 7, 7, generator=g) - 0.3) * 3
+    w_cpu = torch.rand(6, 3, 16, 7, 7, generator=g)
+    x_ref = x_cpu.clone().requires_grad_(True)
+    s_ref, v_ref = O.lif_multi_step_train(x_ref, None, 2.0, 1.0, vr, decay, detach, 2.0)
+    ((s_ref * w_cpu).sum() + (v_ref * 0.3).sum()).backward()
+    n = neuron.LIFNode(tau=2.0, decay_input=decay, v_threshold=1.0, v_reset=vr, surrogate_function=surrogate.ATan(),
+                       detach_reset=detach, step_mode="m").train()
+    x = x_cpu.cuda().requires_grad_(True)
+    s = n(x)
+    ((s * w_cpu.cuda()).sum() + (n.v * 0.3).sum()).backward()
+    assert torch.equal(s.detach().cpu(), s_ref.detach())
+    assert torch.allclose(x.grad.cpu(), x_ref.grad, rtol=1e-5, atol=1e-7)
+    # a second call continues from (and back-propagates into) the stored state, like the reference
+    s2 = n(x)
+    assert s2.requires_grad and n.v.requires_grad
