@@ -33,6 +33,9 @@ WORKLOADS = {
                  K=128, hw=8, in_dim=3),
     "cfg4": dict(desc="KMNIST/Letters-shape 28x28 sampling, b=512 per GPU, T=8, K=512, 49 steps + decode", b=512, T=8,
                  K=512, hw=7, in_dim=1),
+    # the reference as shipped: T=16 (hard-coded), 16 samples per sample() call x 2 (R/main.py:383-387)
+    "ref16": dict(desc="reference as shipped: 28x28 sampling, b=32, T=16, K=128, 49 steps + decode", b=32, T=16, K=128,
+                  hw=7, in_dim=1),
 }
 
 
