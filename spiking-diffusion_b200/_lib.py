@@ -18,7 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libsd_b200.so")
 SOURCES = ["lif.cu", "vq.cu", "conv_simt.cu", "conv_tc.cu", "sample.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--extended-lambda",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--shared", "-cudart", "shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 
 # Exported symbols of include/sd_b200.h (tests check that the library exports exactly these).
 SYMBOLS = [
@@ -57,8 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f not in ("--shared",)] + ["-c", os.path.join(CSRC, src), "-o", obj]
-        cmd = [c for c in cmd if c not in ("-cudart", "shared")]
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:

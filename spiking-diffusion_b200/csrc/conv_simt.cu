@@ -10,6 +10,7 @@
 // Mapping: one thread = one output neuron (b, oy, ox, co) for ALL T timesteps; co is the fastest index in a
 // warp so packed weights [tap][ci][co] are read coalesced and the input element is a warp-wide broadcast.
 // Spike inputs are read 8 channels (16 B) at a time from the STF planes.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace sd {
@@ -25,7 +26,6 @@ struct SimtParams {
   void* out;
   __half* out_sum;
   MemoutCoef coef;
-  float decay_keep;
 };
 
 template <int TMAX>
@@ -525,7 +525,6 @@ int sd_conv_lif_simt(const sd_conv_desc* d, const sd_conv_args* a, void* stream)
   p.v = a->v; p.out = a->out; p.out_sum = (__half*)a->out_sum;
   for (int t = 0; t < SD_MAX_T; ++t)
     p.coef.c[t] = (a->memout_coef_host && t < d->T) ? a->memout_coef_host[t] : 0.f;
-  p.decay_keep = 0.f;
   int64_t n = (int64_t)d->B * d->H_out * d->W_out * d->C_out;
   int64_t blocks = (n + 255) / 256;
   int64_t cap = (int64_t)sm_count() * 16;
@@ -542,7 +541,8 @@ int sd_conv_lif_simt(const sd_conv_desc* d, const sd_conv_args* a, void* stream)
     SD_LAUNCH_CHECK();
     return SD_OK;
   }
-  if (d->in_kind == SD_IN_STF && d->in_T == d->T && d->T <= 8 &&
+  static const bool force_generic = getenv("SD_SIMT_GENERIC") != nullptr;   // debugging aid: exact-order generic kernel
+  if (!force_generic && d->in_kind == SD_IN_STF && d->in_T == d->T && d->T <= 8 &&
       (d->out_kind == SD_OUT_MEMOUT_TANH || (d->out_kind == SD_OUT_LIF && d->C_out % 8 == 0))) {
     int64_t n8 = (int64_t)d->B * d->H_out * d->W_out * ((d->C_out + 7) / 8);
     int64_t bl = (n8 + 127) / 128;

@@ -32,6 +32,7 @@
 //   warp 10    MMA issuer  (one lane issues tcgen05.mma, tcgen05.commit releases stages)
 //   warp 11    TMEM allocator
 #include <stdlib.h>
+#include <mutex>
 #include "common.cuh"
 
 namespace sd {
@@ -513,6 +514,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
 // ---------------------------------------------------------------------------------------------------
 // Configuration (shared by weight packing and launch)
 // ---------------------------------------------------------------------------------------------------
+// Experiment knobs (SD_TC_*) are read from the environment on every call: they are only consulted while a plan is
+// being built (weight packing) and at launch, where they must agree, and getenv is ~100 ns.
 static int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return s ? atoi(s) : dflt;
@@ -710,6 +713,9 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
   if (rc) return rc;
   SD_REQUIRE(a && a->in && a->weights && a->scale && a->shift && a->out, "null pointer argument");
   if (d->C_in0 < d->C_in) SD_REQUIRE(a->in2 != nullptr, "conv_tc: in2 missing for concat");
+  SD_REQUIRE((((uintptr_t)a->in | (uintptr_t)a->in2 | (uintptr_t)a->weights | (uintptr_t)a->out | (uintptr_t)a->out_sum |
+               (uintptr_t)a->v | (uintptr_t)a->workspace | (uintptr_t)a->scale | (uintptr_t)a->shift) & 15) == 0,
+             "conv_tc: every buffer must be 16-byte aligned (cp.async.bulk / 128-bit accesses)");
   SD_DEVICE_OR_RETURN();
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -743,12 +749,13 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
   cudaStream_t st = as_stream(stream);
 #define SD_TC_LAUNCH(NS, KS)                                                                                       \
   do {                                                                                                             \
-    static bool attr_set = false;                                                                                  \
-    if (!attr_set) {                                                                                               \
-      SD_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<NS, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                   227 * 1024));                                                                   \
-      attr_set = true;                                                                                             \
-    }                                                                                                              \
+    static std::once_flag once;                                                                                    \
+    static cudaError_t attr_rc = cudaSuccess;                                                                      \
+    std::call_once(once, [] {                                                                                      \
+      attr_rc = cudaFuncSetAttribute(conv3x3_tc_kernel<NS, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                     227 * 1024);                                                                  \
+    });                                                                                                            \
+    SD_CUDA(attr_rc);                                                                                              \
     conv3x3_tc_kernel<NS, KS><<<grid, kTcThreads, c.smem_bytes, st>>>(p);                                          \
   } while (0)
   const int ks = c.KBLK / 16;

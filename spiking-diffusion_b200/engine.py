@@ -19,9 +19,6 @@ import torch
 from . import _lib
 from ._lib import ConvArgs, ConvDesc, check, lib, ptr, stream_ptr
 
-BN_EPS_DEFAULT = 1e-5
-
-
 def _require_cuda(t: torch.Tensor, what: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"{what} must be a CUDA tensor: spiking_diffusion_b200 has no CPU path "

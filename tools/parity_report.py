@@ -1,0 +1,79 @@
+"""Parity report (GPU box): per-layer firing rates, spike flips, margin histograms and index / image / logit errors
+of the CUDA path against the CPU oracle, for BASELINE config 1 (VQ-VAE E->Q->D, B=64, T=4) and the denoiser."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from conftest import make_denoiser, make_vqvae  # noqa: E402
+from oracle import snn_oracle as O  # noqa: E402
+from spiking_diffusion_b200 import engine, synth  # noqa: E402
+
+EDGES = [0, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1, float("inf")]
+
+
+def hist(m):
+    m = m.flatten()
+    return " ".join(f"{int(((m >= lo) & (m < hi)).sum()):>9d}" for lo, hi in zip(EDGES[:-1], EDGES[1:]))
+
+
+def layer_rows(got, tr, names):
+    print(f"{'layer':6s} {'neurons x T':>12s} {'rate ref':>9s} {'rate ours':>9s} {'flips':>7s} {'flips, no near-thr':>18s}   "
+          "margin |h - v_th| histogram  [0,1e-6) [1e-6,1e-5) [1e-5,1e-4) [1e-4,1e-3) [1e-3,1e-2) [1e-2,1e-1) [1e-1,inf)")
+    for n in names:
+        s_ref, h = tr[n]
+        marg = O.spike_margin(h)
+        diff = got[n] != s_ref
+        # a neuron that came within the margin at step t may differ at every later step too (its reset changed)
+        near = torch.cummax((marg <= 1e-4).to(torch.uint8), dim=0).values.bool()
+        print(f"{n:6s} {s_ref.numel():12d} {float(s_ref.mean()):9.4f} {float(got[n].mean()):9.4f} {int(diff.sum()):7d} "
+              f"{int((diff & ~near).sum()):18d}   {hist(marg)}")
+
+
+def main():
+    torch.manual_seed(0)
+    print("# Parity report, B200 vs CPU oracle (fp32).  Rule: bit-exact where the oracle margin > 1e-4, flip rate <= 1e-4.")
+    print("# 'flips, no near-thr' = flipped neuron-timesteps whose neuron never came within 1e-4 of the threshold at that or an")
+    print("# earlier timestep.  In a multi-layer run these can only be downstream consequences of an upstream near-threshold flip.")
+    for T, B, K in ((4, 64, 128), (8, 32, 512), (16, 8, 128)):
+        m, sd = make_vqvae(T, K, seed=1)
+        img = synth.synth_images(1, B)
+        xs = img.unsqueeze(0).repeat(T, 1, 1, 1, 1)
+        tr = O.Trace()
+        e_ref, rec_ref, idx_ref = O.vqvae_forward_eval(xs, sd, trace=tr)
+        plan = m.plan(T, B, 28, 28)
+        e, rec, idx = plan.forward(img.cuda(), const_over_T=True)
+        bufs = {"enc1": (plan.s1, plan.e1), "enc2": (plan.s2, plan.e2), "enc3": (plan.s3, plan.e3), "gen": (plan.sg, plan.gen),
+                "dec1": (plan.sd1, plan.d1), "dec2": (plan.sd2, plan.d2)}
+        got = {k: engine.stf_to_nchw(b, l.T, l.B, l.C_out, l.H_out, l.W_out).cpu() for k, (b, l) in bufs.items()}
+        print(f"\n## SNN_VQVAE.forward eval, B={B}, T={T}, K={K} (BASELINE config 1 shape when B=64, T=4)")
+        layer_rows(got, tr, list(bufs))
+        gap = O.vq_margin(tr["feat"].reshape(-1, 16), sd["vq_layer.embeddings.weight"])
+        bad = idx.cpu() != idx_ref
+        print(f"VQ indices: {idx_ref.numel()} tokens, {idx_ref.unique().numel()} distinct codes, mismatches {int(bad.sum())}, "
+              f"mismatches with gap > 1e-4: {int((bad & (gap > 1e-4)).sum())};  distance-gap histogram {hist(gap)}")
+        print(f"reconstruction max-abs error {float((rec.cpu() - rec_ref).abs().max()):.3e} (tolerance 1e-3)")
+    for T, b, K, hw, nsplit in ((4, 16, 128, 7, 2), (4, 16, 128, 7, 1), (8, 8, 512, 7, 2), (4, 8, 128, 8, 2), (16, 4, 128, 7, 2)):
+        m, sd = make_denoiser(T, K, seed=2)
+        m.nsplit = nsplit
+        g = torch.Generator().manual_seed(5)
+        x = torch.randint(0, K, (b, 1, hw, hw), generator=g).float()
+        x[torch.rand(b, 1, hw, hw, generator=g) < 0.5] = K
+        t = torch.randint(1, hw * hw + 1, (b,), generator=g)
+        tr = O.Trace()
+        lg_ref = O.denoiser_forward(x, t, sd, T, trace=tr)
+        lg = m(x.cuda(), t.cuda()).cpu()
+        p = m.plan(b, hw, hw)
+        bufs = {"den1": (p.x1, p.l1), "den2": (p.x2, p.l2), "den3": (p.x3, p.l3), "den4": (p.x4, p.l4), "den5": (p.x5, p.l5)}
+        got = {k: engine.stf_to_nchw(bf, l.T, l.B, l.C_out, l.H_out, l.W_out).cpu() for k, (bf, l) in bufs.items()}
+        print(f"\n## DummyModel.forward, b={b}, T={T}, K={K}, latent {hw}x{hw}, fp16 weight terms = {nsplit}"
+              + ("  (NOT the parity configuration)" if nsplit == 1 else ""))
+        layer_rows(got, tr, list(bufs))
+        print(f"logits max-abs error {float((lg - lg_ref).abs().max()):.3e}, logits abs max {float(lg_ref.abs().max()):.2f}")
+
+
+if __name__ == "__main__":
+    main()
