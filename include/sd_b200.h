@@ -189,6 +189,24 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream);
 /* 1 if sd_conv_lif_tc supports the descriptor on this build. */
 int sd_conv_tc_supported(const sd_conv_desc* d);
 
+/* ---- (f.1) training-path kernels (first correct versions, CUDA cores) ------------------------------------------
+ * The reference trains through torch autograd over F.conv2d / F.conv_transpose2d / F.batch_norm
+ * (SJ/activation_based/layer.py:164-173,316-325,458-465).  The input gradient of a convolution is the adjoint
+ * convolution and is computed with sd_conv_lif_simt (SD_IN_REAL_SEQ -> SD_OUT_REAL_SEQ); these entry points add the
+ * weight/bias gradient and train-mode BatchNorm.
+ * sd_conv_wgrad: d describes the FORWARD op; x fp32 [T,B,C_in,H_in,W_in], grad_out fp32 [T,B,C_out,H_out,W_out];
+ *   grad_w in the reference parameter layout ([C_out,C_in,kh,kw] or [C_in,C_out,kh,kw]), grad_bias [C_out] or NULL.
+ * sd_bn_train_forward: x, y fp32 [n_outer, C, HW]; batch mean / biased variance per channel are written for the
+ *   backward pass and the caller's running-statistics update.
+ */
+int sd_conv_wgrad(const sd_conv_desc* d, const float* x, const float* grad_out, float* grad_w, float* grad_bias_or_null,
+                  void* stream);
+int sd_bn_train_forward(const float* x, const float* gamma_or_null, const float* beta_or_null, float* y,
+                        float* mean_out, float* var_out, int64_t n_outer, int C, int64_t HW, float eps, void* stream);
+int sd_bn_backward(const float* x, const float* grad_out, const float* mean, const float* var,
+                   const float* gamma_or_null, float* grad_x, float* grad_gamma_or_null, float* grad_beta_or_null,
+                   int64_t n_outer, int C, int64_t HW, float eps, void* stream);
+
 /* ---- (a12) absorbing-diffusion sampling step ----------------------------------------------------
  * Torch-compatible Philox4x32-10 streams (TORCH/include/ATen/native/cuda/DistributionTemplates.h:50-87):
  * element li of a call with (seed, offset) is component (li / tpg) % 4 of

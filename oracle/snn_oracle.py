@@ -359,3 +359,80 @@ def vq_margin(flat_x: Tensor, codebook: Tensor) -> Tensor:
     d = vq_distances(flat_x, codebook)
     top2 = torch.topk(d, 2, dim=1, largest=False).values
     return top2[:, 1] - top2[:, 0]
+
+
+# --------------------------------------------------------------------------------------------------
+# Training branches: differentiable restatements, gradients by torch autograd
+# --------------------------------------------------------------------------------------------------
+def conv_bn_train(x_seq: Tensor, p: Params, conv: str, bn: Optional[str], stride: int = 1, padding: int = 0,
+                  transposed: bool = False, output_padding: int = 0) -> Tensor:
+    """Same as conv_bn but BatchNorm in training mode: batch statistics over T*N*H*W (layer.py:458-465 ->
+    F.batch_norm(training=True)); the running buffers in ``p`` are updated in place like nn.BatchNorm2d does."""
+    w, b = p[conv + ".weight"], p.get(conv + ".bias")
+    if transposed:
+        y = _seq(lambda z: F.conv_transpose2d(z, w, b, stride=stride, padding=padding,
+                                             output_padding=output_padding), x_seq)
+    else:
+        y = _seq(lambda z: F.conv2d(z, w, b, stride=stride, padding=padding), x_seq)
+    if bn is not None:
+        y = _seq(lambda z: F.batch_norm(z, p[bn + ".running_mean"], p[bn + ".running_var"], p[bn + ".weight"],
+                                        p[bn + ".bias"], True, 0.1, BN_EPS), y)
+    return y
+
+
+def _layer_train(x_seq, p, conv, bn, **kw):
+    return lif_multi_step_train(conv_bn_train(x_seq, p, conv, bn, **kw))[0]
+
+
+def vqvae_forward_train(x_seq: Tensor, image: Tensor, p: Params, data_variance, commitment_cost: float = 0.25):
+    """R/snn_model/vae_model.py:179-196 training branch with VectorQuantizer.forward :40-85 (num_step := T).
+    Returns (e_q_loss, recon_loss, real_recon_loss)."""
+    T = x_seq.shape[0]
+    q = "encoder.snn_convs."
+    z = _layer_train(x_seq, p, q + "0", q + "1", stride=2, padding=1)
+    z = _layer_train(z, p, q + "3", q + "4", stride=2, padding=1)
+    z = _layer_train(z, p, q + "6", q + "7")
+    alpha, cb = p["vq_layer.alpha"], p["vq_layer.embeddings.weight"]
+    x_memout = (1 - alpha) * memout(z) + alpha * torch.sum(z, dim=0) / T
+    x_memout = x_memout.permute(0, 2, 3, 1).contiguous()
+    flat = x_memout.reshape(-1, cb.shape[1])
+    idx = vq_code_indices(flat, cb)
+    quantized = F.embedding(idx, cb).view_as(x_memout)
+    q_latent_loss = F.mse_loss(quantized, x_memout.detach())
+    e_latent_loss = F.mse_loss(x_memout, quantized.detach())
+    loss_1 = q_latent_loss + commitment_cost * e_latent_loss
+    quantized = x_memout + (quantized - x_memout).detach()
+    quantized = quantized.permute(0, 3, 1, 2).contiguous().unsqueeze(0).repeat(T, 1, 1, 1, 1)
+    quantized = _layer_train(quantized, p, "vq_layer.poisson.0", "vq_layer.poisson.1")
+    q2 = torch.mean((psp(quantized) - psp(z.detach())) ** 2)
+    e2 = torch.mean((psp(quantized.detach()) - psp(z)) ** 2)
+    e_q_loss = loss_1 + q2 + commitment_cost * e2
+    q = "decoder.snn_convs."
+    x = _layer_train(quantized, p, q + "0", q + "1", stride=2, padding=1, transposed=True, output_padding=1)
+    x = _layer_train(x, p, q + "3", q + "4", stride=2, padding=1, transposed=True, output_padding=1)
+    x = conv_bn_train(x, p, q + "6", None, stride=1, padding=1, transposed=True)
+    x_recon = torch.tanh(memout(x))
+    real = F.mse_loss(x_recon, image)
+    return e_q_loss, real / data_variance, real
+
+
+def denoiser_forward_train(x: Tensor, t: Tensor, p: Params, T: int) -> Tensor:
+    """R/snn_model/vq_diffusion.py:189-208 in training mode (batch-statistics BN, surrogate-gradient LIF)."""
+    tt = torch.ones_like(x) * (t.unsqueeze(1).unsqueeze(2).unsqueeze(3))
+    xin = torch.cat((x, tt), dim=1).unsqueeze(0).repeat(T, 1, 1, 1, 1)
+    x1 = _layer_train(xin, p, "conv1.0", "conv1.1", stride=1, padding=1)
+    x5 = x1
+    for i in (2, 3, 4, 5):
+        x5 = _layer_train(x5, p, f"conv{i}.0", f"conv{i}.1", stride=1, padding=1)
+    x6 = conv_bn_train(torch.cat((x5, x1), dim=2), p, "conv6.0", None, stride=1, padding=1)
+    return torch.sum(x6, dim=0) / T
+
+
+def diffusion_train_loss(logits: Tensor, x_0_ignore: Tensor, t: Tensor, num_timesteps: int) -> Tensor:
+    """Re-weighted ELBO of R/snn_model/vq_diffusion.py:86-101 given the denoiser logits."""
+    b, K = logits.shape[0], logits.shape[1]
+    n_tok = logits.shape[2] * logits.shape[3]
+    ce = F.cross_entropy(logits.reshape(b, K, n_tok), x_0_ignore.reshape(b, n_tok).long(), ignore_index=-1,
+                         reduction="none").sum(1)
+    weight = 1 - (t / num_timesteps)
+    return (weight * ce / (math.log(2) * n_tok)).mean()

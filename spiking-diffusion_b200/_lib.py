@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libsd_b200.so")
-SOURCES = ["lif.cu", "vq.cu", "conv_simt.cu", "conv_tc.cu", "sample.cu"]
+SOURCES = ["lif.cu", "vq.cu", "conv_simt.cu", "conv_tc.cu", "sample.cu", "train.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--extended-lambda",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 
@@ -25,7 +25,8 @@ SYMBOLS = [
     "sd_last_error", "sd_version", "sd_device_info", "sd_stf_guard", "sd_stf_rows", "sd_stf_bytes",
     "sd_stf_from_nchw", "sd_stf_to_nchw", "sd_channel_affine", "sd_state_convert", "sd_lif_forward", "sd_lif_backward", "sd_memout", "sd_vq_feature", "sd_vq_lookup",
     "sd_vq_gather", "sd_conv_weight_bytes_simt", "sd_conv_weight_bytes_tc", "sd_conv_workspace_bytes", "sd_conv_pack_weights_simt",
-    "sd_conv_pack_weights_tc", "sd_conv_lif_simt", "sd_conv_lif_tc", "sd_conv_tc_supported", "sd_philox_uniform",
+    "sd_conv_pack_weights_tc", "sd_conv_lif_simt", "sd_conv_lif_tc", "sd_conv_tc_supported", "sd_conv_wgrad",
+    "sd_bn_train_forward", "sd_bn_backward", "sd_philox_uniform",
     "sd_philox_exponential", "sd_philox_offset_increment", "sd_sample_step", "sd_sample_step_dev", "sd_denoiser_input", "sd_to_uint8",
 ]
 
@@ -125,6 +126,9 @@ def _declare(lib: ctypes.CDLL) -> None:
         "sd_conv_lif_simt": (i, [pd, pa, vp]),
         "sd_conv_lif_tc": (i, [pd, pa, vp]),
         "sd_conv_tc_supported": (i, [pd]),
+        "sd_conv_wgrad": (i, [pd, vp, vp, vp, vp, vp]),
+        "sd_bn_train_forward": (i, [vp, vp, vp, vp, vp, vp, i64, i, i64, f, vp]),
+        "sd_bn_backward": (i, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i, i64, f, vp]),
         "sd_philox_uniform": (i, [vp, i64, u64, u64, i64, i64, ctypes.POINTER(u64), vp]),
         "sd_philox_exponential": (i, [vp, i64, u64, u64, i64, i64, ctypes.POINTER(u64), vp]),
         "sd_philox_offset_increment": (i, [i64, ctypes.POINTER(u64)]),

@@ -24,6 +24,90 @@ def _check_5d(x: torch.Tensor):
         raise ValueError(f"expected x with shape [T, N, C, H, W], but got x with shape {x.shape}!")
 
 
+class _ConvSpec:
+    """Minimal stand-in for an nn.Conv2d / nn.ConvTranspose2d (what engine.FusedLayer reads), used to run the adjoint
+    convolution of a layer for its input gradient."""
+
+    def __init__(self, weight, transposed, kernel_size, stride, padding, output_padding):
+        self.weight, self.bias, self.transposed = weight, None, transposed
+        self.kernel_size, self.stride, self.padding = kernel_size, stride, padding
+        self.output_padding, self.dilation, self.groups = output_padding, (1, 1), 1
+
+
+class _ConvFn(torch.autograd.Function):
+    """Conv2d / ConvTranspose2d on [T, N, C, H, W] with gradients: forward and input gradient through the CUDA-core
+    conv kernel (the input gradient of a convolution is the adjoint convolution with the same weights), weight /
+    bias gradient through sd_conv_wgrad.  Mirrors torch autograd over F.conv2d / F.conv_transpose2d
+    (SJ/activation_based/layer.py:164-173, 316-325)."""
+
+    @staticmethod
+    def forward(ctx, x5, weight, bias, mod):
+        T, B, _, H, W = x5.shape
+        plan = engine.FusedLayer(mod, None, None, T=T, B=B, H_in=H, W_in=W, in_kind=_lib.IN_REAL_SEQ,
+                                 out_kind=_lib.OUT_REAL_SEQ, impl="simt")
+        x5 = x5.contiguous().float()
+        y = plan.run(x5, plan.alloc_out())
+        ctx.save_for_backward(x5, weight)
+        ctx.meta = (plan.desc, bool(mod.transposed), tuple(mod.kernel_size), tuple(mod.stride), tuple(mod.padding),
+                    bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x5, weight = ctx.saved_tensors
+        d, transposed, ks, stride, padding, has_bias = ctx.meta
+        gy = gy.contiguous().float()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            if transposed:   # adjoint of conv_transpose2d(x, w) is conv2d(gy, w): w [C_in, C_out, k, k] read as [out, in, k, k]
+                spec = _ConvSpec(weight.detach(), False, ks, stride, padding, (0, 0))
+            else:            # adjoint of conv2d(x, w) is conv_transpose2d(gy, w) sized back to the input
+                op = d.H_in - ((d.H_out - 1) * stride[0] - 2 * padding[0] + ks[0])
+                spec = _ConvSpec(weight.detach(), True, ks, stride, padding, (op, op))
+            adj = engine.FusedLayer(spec, None, None, T=d.T, B=d.B, H_in=d.H_out, W_in=d.W_out, in_kind=_lib.IN_REAL_SEQ,
+                                    out_kind=_lib.OUT_REAL_SEQ, impl="simt")
+            gx = adj.run(gy, adj.alloc_out())
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            gw = torch.empty_like(weight, dtype=torch.float32)
+            gb = torch.empty(d.C_out, dtype=torch.float32, device=gy.device) if has_bias else None
+            import ctypes
+            check(lib().sd_conv_wgrad(ctypes.byref(d), ptr(x5), ptr(gy), ptr(gw), ptr(gb), stream_ptr()))
+        return gx, gw, gb, None
+
+
+class _BNFn(torch.autograd.Function):
+    """Train-mode BatchNorm2d over [n_outer, C, H, W] (batch statistics), forward and backward on our kernels."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        x = x.contiguous().float()
+        n_outer, C = x.shape[0], x.shape[1]
+        hw = x.shape[2] * x.shape[3]
+        y = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        var = torch.empty(C, dtype=torch.float32, device=x.device)
+        check(lib().sd_bn_train_forward(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(var), n_outer, C, hw,
+                                        float(eps), stream_ptr()))
+        ctx.save_for_backward(x, mean, var, gamma if gamma is not None else torch.empty(0, device=x.device))
+        ctx.meta = (float(eps), gamma is not None, beta is not None)
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    def backward(ctx, gy, _gm, _gv):
+        x, mean, var, gamma = ctx.saved_tensors
+        eps, has_g, has_b = ctx.meta
+        gy = gy.contiguous().float()
+        n_outer, C = x.shape[0], x.shape[1]
+        hw = x.shape[2] * x.shape[3]
+        gx = torch.empty_like(x)
+        gg = torch.empty(C, dtype=torch.float32, device=x.device)
+        gb = torch.empty(C, dtype=torch.float32, device=x.device)
+        check(lib().sd_bn_backward(ptr(x), ptr(gy), ptr(mean), ptr(var), ptr(gamma) if has_g else None, ptr(gx), ptr(gg),
+                                   ptr(gb), n_outer, C, hw, eps, stream_ptr()))
+        return gx, (gg if has_g else None), (gb if has_b else None), None
+
+
 class _ConvMixin(base.StepModule):
     def _plan(self, T, B, H, W) -> engine.FusedLayer:
         key = (T, B, H, W, self.weight.data_ptr(), self.weight._version,
@@ -37,8 +121,7 @@ class _ConvMixin(base.StepModule):
     def _forward_any(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:
             raise RuntimeError("layer forward needs CUDA tensors: spiking_diffusion_b200 has no CPU path")
-        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad) and self.training:
-            raise NotImplementedError("training (autograd) is not implemented in this round (SURVEY.md 8(f) rank 1)")
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad)
         if self.step_mode == "s":
             if x.dim() != 4:
                 raise ValueError(f"expected x with shape [N, C, H, W], but got x with shape {x.shape}!")
@@ -47,9 +130,12 @@ class _ConvMixin(base.StepModule):
             _check_5d(x)
             x5 = x
         T, B, _, H, W = x5.shape
-        plan = self._plan(T, B, H, W)
-        out = plan.alloc_out()
-        plan.run(x5.contiguous().float(), out)
+        if needs_grad:
+            out = _ConvFn.apply(x5, self.weight, self.bias, self)
+        else:
+            plan = self._plan(T, B, H, W)
+            out = plan.alloc_out()
+            plan.run(x5.contiguous().float(), out)
         return out[0] if self.step_mode == "s" else out
 
 
@@ -91,12 +177,22 @@ class BatchNorm2d(nn.BatchNorm2d, base.StepModule):
     def forward(self, x: torch.Tensor):
         if not x.is_cuda:
             raise RuntimeError("layer forward needs CUDA tensors: spiking_diffusion_b200 has no CPU path")
-        if self.training or not self.track_running_stats:
-            raise NotImplementedError("train-mode BatchNorm (batch statistics) is not implemented in this round")
         if self.step_mode == "m":
             _check_5d(x)
         elif x.dim() != 4:
             raise ValueError(f"expected x with shape [N, C, H, W], but got x with shape {x.shape}!")
+        if self.training or not self.track_running_stats:
+            # batch statistics over T*N*H*W (functional.seq_to_ann_forward flattens T into the batch, layer.py:458-465)
+            x4 = x.flatten(0, 1) if x.dim() == 5 else x
+            y, mean, var = _BNFn.apply(x4, self.weight, self.bias, self.eps)
+            if self.track_running_stats:
+                with torch.no_grad():   # F.batch_norm's running update: momentum, unbiased variance
+                    n = x4.numel() // x4.shape[1]
+                    self.num_batches_tracked += 1
+                    mom = self.momentum if self.momentum is not None else 1.0 / float(self.num_batches_tracked)
+                    self.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
+                    self.running_var.mul_(1 - mom).add_(var * (n / max(n - 1, 1)), alpha=mom)
+            return y.view(x.shape)
         scale, shift = engine.fold_bn(None, self.num_features, self, x.device)
         xc = x.contiguous().float()
         out = torch.empty_like(xc)
@@ -154,8 +250,12 @@ class SpikingSequential(nn.Sequential):
         if not x.is_cuda:
             raise RuntimeError("SpikingSequential.forward needs CUDA tensors: spiking_diffusion_b200 has no CPU path")
         _check_5d(x)
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("training (autograd) is not implemented in this round (SURVEY.md 8(f) rank 1)")
+        if self.training:
+            # training: layer by layer through the autograd-capable kernels (conv, train-mode BN, surrogate LIF), exactly
+            # the reference's nn.Sequential; the fused inference kernels fold BN running statistics and have no backward
+            for m in self:
+                x = m(x)
+            return x
         T, B, _, H, W = x.shape
         key = (T, B, H, W, x.device, tuple(p._version for p in self.parameters()),
                tuple(b._version for b in self.buffers()))

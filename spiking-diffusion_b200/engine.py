@@ -71,7 +71,7 @@ class FusedLayer:
         L = lib()
         w = conv.weight.detach()
         _require_cuda(w, "layer weights")
-        transposed = isinstance(conv, torch.nn.ConvTranspose2d)
+        transposed = bool(getattr(conv, "transposed", isinstance(conv, torch.nn.ConvTranspose2d)))
         kh, kw = conv.kernel_size
         stride, pad = conv.stride[0], conv.padding[0]
         if conv.stride[0] != conv.stride[1] or conv.padding[0] != conv.padding[1]:

@@ -31,6 +31,10 @@ class MembraneOutputLayer(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("MembraneOutputLayer.forward needs CUDA tensors: there is no CPU path")
         T = x.shape[0]
+        if torch.is_grad_enabled() and x.requires_grad:
+            # training: a T-term weighted sum; kept as tensor algebra so that autograd provides the backward
+            out = torch.sum(x * self.coef, dim=0)
+            return torch.tanh(out) if apply_tanh else out
         coef = self.coef_host(T)
         xc = x.contiguous().float()
         out = torch.empty(xc.shape[1:], dtype=torch.float32, device=x.device)

@@ -6,12 +6,15 @@ Differences from the reference, all additive:
 * ``VectorQuantizer.forward_with_loss`` offers the (quantized, loss, indices) 3-tuple named in the north star;
   ``forward`` keeps the reference's mode-dependent 2-tuple because its callers unpack two values
   (vae_model.py:184,189).
-* training mode raises NotImplementedError (surrogate-gradient BPTT is SURVEY.md section 8(f) rank 1).
+* training mode runs layer by layer through the autograd-capable kernels
+  (conv forward / adjoint / weight-gradient, train-mode BatchNorm, surrogate-gradient LIF); the loss algebra
+  (MSE, straight-through estimator, PSP, tanh) is plain tensor arithmetic as in the reference.
 """
 import ctypes
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from .. import _lib, engine
 from .._lib import check, lib, ptr, stream_ptr
@@ -52,11 +55,13 @@ class VectorQuantizer(nn.Module):
         return z
 
     def forward(self, x: torch.Tensor):
-        """x: [T, N, D, h, w] spikes.  eval -> (spikes [T,N,D,h,w], indices [N*h*w] int64)  (vae_model.py:53-58)."""
-        _no_training(self)
+        """x: [T, N, D, h, w] spikes.  eval -> (spikes [T,N,D,h,w], indices [N*h*w] int64)  (vae_model.py:53-58);
+        train -> (spikes, loss_1 + loss_2)  (vae_model.py:61-85)."""
         if x.dim() != 5:
             raise ValueError(f"expected x with shape [T, N, C, H, W], but got x with shape {x.shape}!")
         T = x.shape[0]
+        if self.training:
+            return self._forward_train(x)
         x_memout = self.feature(x)
         flat_x = x_memout.reshape(-1, self.embedding_dim)
         encoding_indices = self.get_code_indices(flat_x)
@@ -65,6 +70,26 @@ class VectorQuantizer(nn.Module):
         quantized = torch.unsqueeze(quantized, dim=0).expand(T, -1, -1, -1, -1)
         quantized = self.poisson(quantized)
         return quantized, encoding_indices
+
+    def _forward_train(self, x: torch.Tensor):
+        """Training branch, operation for operation as vae_model.py:42-85 with num_step := T."""
+        T = x.shape[0]
+        x_memout = (1 - self.alpha) * self.memout(x) + self.alpha * torch.sum(x, dim=0) / T
+        x_memout = x_memout.permute(0, 2, 3, 1).contiguous()
+        flat_x = x_memout.reshape(-1, self.embedding_dim)
+        encoding_indices = self.get_code_indices(flat_x.detach())          # argmin: no gradient
+        quantized = F.embedding(encoding_indices, self.embeddings.weight).view_as(x_memout)
+        q_latent_loss = F.mse_loss(quantized, x_memout.detach())
+        e_latent_loss = F.mse_loss(x_memout, quantized.detach())
+        loss_1 = q_latent_loss + self.commitment_cost * e_latent_loss
+        quantized = x_memout + (quantized - x_memout).detach()             # straight-through estimator
+        quantized = quantized.permute(0, 3, 1, 2).contiguous()
+        quantized = torch.unsqueeze(quantized, dim=0).repeat(T, 1, 1, 1, 1)
+        quantized = self.poisson(quantized)
+        q_latent_loss_2 = torch.mean((self.psp(quantized) - self.psp(x.detach())) ** 2)
+        e_latent_loss_2 = torch.mean((self.psp(quantized.detach()) - self.psp(x)) ** 2)
+        loss_2 = q_latent_loss_2 + self.commitment_cost * e_latent_loss_2
+        return quantized, loss_1 + loss_2
 
     def forward_with_loss(self, x: torch.Tensor):
         """(quantized, loss, indices): eval-mode loss is the VQ objective value, for monitoring only."""
@@ -121,7 +146,6 @@ class Encoder(nn.Module):
         )
 
     def forward(self, x):
-        _no_training(self)
         return self.snn_convs(x)  # [t, b, c, h, w]
 
 
@@ -146,7 +170,6 @@ class Decoder(nn.Module):
         )
 
     def forward(self, x):
-        _no_training(self)
         return self.snn_convs(x)  # [t, b, c, h, w]
 
 
@@ -175,13 +198,20 @@ class SNN_VQVAE(nn.Module):
         return self._plans["plan"]
 
     def forward(self, x, image):
-        """x: [T, B, C, H, W].  eval -> (e, x_recon, encoding_indices)   (vae_model.py:181-187)."""
-        _no_training(self)
+        """x: [T, B, C, H, W].  eval -> (e, x_recon, encoding_indices)   (vae_model.py:181-187);
+        train -> (e_q_loss, recon_loss, real_recon_loss)                   (vae_model.py:189-196)."""
         z = self.encoder(x)
-        e, enco = self.vq_layer(z)
+        if not self.training:
+            e, enco = self.vq_layer(z)
+            x_recon = self.decoder(e)
+            x_recon = self.memout(x_recon, apply_tanh=True)
+            return e, x_recon, enco
+        e, e_q_loss = self.vq_layer(z)
         x_recon = self.decoder(e)
-        x_recon = self.memout(x_recon, apply_tanh=True)
-        return e, x_recon, enco
+        x_recon = torch.tanh(self.memout(x_recon))
+        real_recon_loss = F.mse_loss(x_recon, image)
+        recon_loss = real_recon_loss / self.data_variance
+        return e_q_loss, recon_loss, real_recon_loss
 
     @torch.no_grad()
     def decode_indices(self, sample: torch.Tensor, T: int = None) -> torch.Tensor:

@@ -89,10 +89,16 @@ class DummyModel(nn.Module):
         The whole network runs as one fused chain, so the per-layer LIF states are consumed inside the kernels:
         this equals the reference whenever the net is reset between calls, which every reference call site does
         (vq_diffusion.py:129, R/main.py:249,391)."""
-        if self.training:
-            raise NotImplementedError("training mode is not implemented in this round (SURVEY.md section 8(f) rank 1)")
         if not x.is_cuda:
             raise RuntimeError("DummyModel.forward needs CUDA tensors: there is no CPU path")
+        if self.training:
+            # training: the reference's layer-by-layer graph (vq_diffusion.py:195-206) on the autograd-capable kernels
+            tt = torch.ones_like(x) * (t.unsqueeze(1).unsqueeze(2).unsqueeze(3))
+            xin = torch.cat((x, tt), dim=1).unsqueeze(dim=0).repeat(self.T, 1, 1, 1, 1)
+            x1 = self.conv1(xin)
+            x5 = self.conv5(self.conv4(self.conv3(self.conv2(x1))))
+            x6 = self.conv6(torch.cat((x5, x1), dim=2))
+            return torch.sum(x6, dim=0) / self.T
         for m in self.modules():
             if isinstance(m, neuron.LIFNode) and isinstance(m.v, torch.Tensor):
                 raise RuntimeError("DummyModel.forward starts from reset LIF state; call functional.reset_net(model) first")
@@ -134,8 +140,27 @@ class AbsorbingDiffusion(Sampler):
         return x_t, x_0_ignore, mask
 
     def _train_loss(self, x_0):
-        raise NotImplementedError("the diffusion training loss needs the denoiser backward pass "
-                                  "(SURVEY.md section 8(f) rank 1, not in this round)")
+        """Re-weighted ELBO of the absorbing diffusion (vq_diffusion.py:75-101); x_0: [b, 1, h, w] token ids."""
+        b, device = x_0.size(0), x_0.device
+        n_tok = self.shape[0] * self.shape[1]
+        t, pt = self.sample_time(b, device)
+        x_t, x_0_ignore, mask = self.q_sample(x_0=x_0, t=t)
+        x_0_hat_logits = self._denoise_fn(x_t, t=t)
+        cross_entropy_loss = F.cross_entropy(x_0_hat_logits.reshape(b, self.num_classes, n_tok),
+                                             x_0_ignore.reshape(b, n_tok).long(), ignore_index=-1,
+                                             reduction='none').sum(1)
+        vb_loss = cross_entropy_loss / t
+        vb_loss = vb_loss / pt
+        vb_loss = vb_loss / (math.log(2) * x_0.shape[1:].numel())
+        if self.loss_type == 'elbo':
+            loss = vb_loss
+        elif self.loss_type == 'reweighted_elbo':
+            weight = (1 - (t / self.num_timesteps))
+            loss = weight * cross_entropy_loss
+            loss = loss / (math.log(2) * x_0.shape[1:].numel())
+        else:
+            raise ValueError
+        return loss.mean()
 
     def train_iter(self, x):
         return {"loss": self._train_loss(x)}

@@ -151,8 +151,6 @@ def test_denoiser_vs_oracle(T, b, K, hw, nsplit):
     assert rate <= (FLIP_RATE_MAX if nsplit == 2 else 3e-2), rate
     if flips == 0:
         assert float((lg - lg_ref).abs().max()) <= 1e-4
-    with pytest.raises(NotImplementedError):
-        m.train()(x.cuda(), t.cuda())
 
 
 def test_get_data_for_diff_reproduces_the_no_reset_state_leak():

@@ -108,8 +108,8 @@ def test_cpu_tensors_are_rejected_not_silently_computed():
         m(torch.zeros(4, 1, 1, 28, 28), torch.zeros(1, 1, 28, 28))
     with pytest.raises(RuntimeError, match="no CPU path"):
         DummyModel(1, 128, T=4).eval()(torch.zeros(1, 1, 7, 7), torch.ones(1).long())
-    with pytest.raises(NotImplementedError):
-        SNN_VQVAE(1, 16, 128, 1.0)(torch.zeros(16, 1, 1, 28, 28), None)      # train mode: not this round
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        SNN_VQVAE(1, 16, 128, 1.0)(torch.zeros(16, 1, 1, 28, 28), torch.zeros(1, 1, 28, 28))   # train mode, CPU tensors
 
 
 def test_absorbing_diffusion_attributes():
