@@ -554,6 +554,17 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
   else if (c->T_acc * 128 <= 512) n_tile = 128;
   else if (c->T_acc * 64 <= 512) n_tile = 64;
   else n_tile = 32;
+  {
+    // Small batches: with N = 128 there are fewer tiles than SMs (the reference samples 16 images per call: 7 M tiles).
+    // Halve N while that at least doubles the number of busy SMs; each tile then also gets a second TMEM stage.
+    check_device();
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const int64_t rows = (int64_t)d->B * d->H_in * d->W_in;
+    const int m_tiles = (int)((rows + kTileRows - 1) / kTileRows);
+    while (n_tile > 32 && env_int("SD_TC_SMALL_BATCH_SPLIT", 1) &&
+           (int64_t)m_tiles * ((d->C_out + n_tile - 1) / n_tile) * 2 <= sms && d->C_out > n_tile / 2)
+      n_tile /= 2;
+  }
   n_tile = env_int("SD_TC_NTILE", n_tile);
   while (n_tile > 32 && n_tile / 2 >= d->C_out) n_tile /= 2;
   if (!(n_tile == 32 || n_tile == 64 || n_tile == 128 || n_tile == 256) || c->T_acc * n_tile > 512) {
@@ -581,7 +592,11 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
       if (c0 % kblk || c1 % kblk) continue;
       c->a_stage_bytes = (uint32_t)c->T_acc * (kblk / 8) * ndx * c->rows_ld * 16;
       c->b_stage_bytes = (uint32_t)d->nsplit * (kblk / 8) * n_tile * 16;
-      if (2 * c->a_stage_bytes + 4 * c->b_stage_bytes + 1024 > kSmemBudget) continue;
+      // The K block fixes the fp32 accumulation order ((channel block, tap, 16-channel step)), so it must not depend
+      // on the batch size: the fit test uses the N = 128 stage size even when a small batch runs narrower tiles.
+      // A batch shard then reproduces the unsharded result bit for bit.
+      const uint32_t b_ref = (uint32_t)d->nsplit * (kblk / 8) * (n_tile > 128 ? n_tile : 128) * 16;
+      if (2 * c->a_stage_bytes + 4 * b_ref + 1024 > kSmemBudget) continue;
       c->KBLK = kblk;
       found = true;
     }

@@ -249,6 +249,8 @@ class SamplerPlan:
         import os
         if n_streams is None:
             n_streams = int(os.environ.get("SD_SAMPLER_STREAMS", "2"))
+        if b < 64:
+            n_streams = 1          # small batches do not fill the SMs even once: sub-batches would only add launches
         n_streams = max(1, min(n_streams, b))
         self.mask_id = int(mask_id)
         self.b, self.h, self.w, self.K = b, h, w, model.num_embeddings
