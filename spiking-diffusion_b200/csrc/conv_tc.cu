@@ -15,10 +15,12 @@
 // is just a different 16-byte-aligned start address in the A descriptor: the input tile is loaded ONCE per K-block
 // and reused by all 9 taps (9x less L2->SMEM traffic than im2col).
 //
-//   M tile  = 128 consecutive rows of the flat pixel sequence (tiles may straddle images), all T timesteps
-//   N tile  = 32..128 output channels
-//   K block = 16..64 input channels, x 9 taps, x nsplit fp16 weight terms
-//   D       = T accumulators of [128 x N] fp32 resident in TMEM (T*N <= 512 columns, x2 stages when they fit)
+//   M tile  = 128 consecutive rows of the flat pixel sequence (tiles may straddle images)
+//   N tile  = 128 output channels (64 / 32 when a small batch would leave most SMs without a tile)
+//   K block = 32 input channels (64 for the linear read-out), x 9 taps, x nsplit fp16 weight terms
+//   D       = one [128 x N] fp32 accumulator per timestep, up to 4 timesteps resident in TMEM (512 columns, two
+//             stages when N <= 64).  T <= 4: one pass, the membrane potential stays in registers.  T = 8 / 16: 2 / 4
+//             passes of 4 timesteps over the same tile, potential and spike counts carried in an L2-resident plane.
 //
 // Exactness.  Spikes (and T-summed spike counts) are exact in fp16.  Each fp32 weight is scaled by an exact
 // per-output-channel power of two and split into nsplit fp16 terms (hi, lo = 22 significant bits for
