@@ -548,11 +548,19 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
     const int tacc = env_int("SD_TC_TACC", 0);           // experiment knob: timesteps per pass
     if (tacc > 0 && tacc <= d->T && d->T % tacc == 0) c->T_acc = tacc;
   }
+  // Layers with exactly 256 output channels have only two N = 128 tiles per M tile, which quantises badly on 148 SMs
+  // (98 M tiles -> 196 tiles -> 2 waves, the second one a third full).  One N = 256 tile per M tile with 2 timesteps
+  // per pass does the same work in a single wave and fetches the A operand half as often per output column.
+  bool wide = false;
+  if (d->out_kind == SD_OUT_LIF && d->C_out == 256 && d->T % 2 == 0 && d->T <= 4 && env_int("SD_TC_WIDE256", 0)) {
+    c->T_acc = 2;
+    wide = true;
+  }
   c->n_tchunks = d->out_kind == SD_OUT_LIF ? d->T / c->T_acc : 1;
   int n_tile;
   // Larger N amortises the A-operand fetch from shared memory (4 KB per MMA whatever N is): measured on B200,
   // N = 128 without epilogue overlap beats N = 64 with two TMEM stages (profiles/).
-  if (c->T_acc * 256 <= 512 && d->C_out >= 256 && env_int("SD_TC_N256", 0)) n_tile = 256;
+  if (c->T_acc * 256 <= 512 && d->C_out >= 256 && (wide || env_int("SD_TC_N256", 0))) n_tile = 256;
   else if (c->T_acc * 128 <= 512) n_tile = 128;
   else if (c->T_acc * 64 <= 512) n_tile = 64;
   else n_tile = 32;
