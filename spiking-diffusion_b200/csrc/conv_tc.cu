@@ -27,12 +27,19 @@
 // nsplit = 2); every product is exact and accumulation is fp32 in the tensor core.  Both terms accumulate into
 // the same TMEM accumulator (the A tile is shared, only the B descriptor changes).
 //
+// CTA pairs.  By default two CTAs of a cluster (two SMs of a TPC) compute one M = 256 tile with
+// tcgen05.mma.cta_group::2: each SM stages its own 128 A rows and HALF of the B block, so the shared-memory operand
+// fetch per SM drops from 8 KB to 6 KB per 64-cycle MMA (measured +20-25 % per layer, profiles/r01_experiments.md).
+// The leader CTA issues the MMAs; the peer's relay warp forwards "stage landed" to the leader's barriers with remote
+// mbarrier arrives, tcgen05.commit multicasts stage releases and "accumulator ready" to both CTAs, and the peer's
+// epilogue releases the accumulator with a remote arrive.
+//
 // Warp roles (384 threads, 1 CTA / SM, persistent over tiles):
 //   warps 0-7  epilogue: tcgen05.ld -> BN affine -> LIF over all T in registers -> fp16 spikes / T-sum / v
 //   warp  8    A producer  (cp.async.bulk global -> shared, one copy per (t, chunk) plane, mbarrier tx)
 //   warp  9    B producer  (cp.async.bulk of one pre-packed [split][chunk][n][8] weight block per tap)
 //   warp 10    MMA issuer  (one lane issues tcgen05.mma, tcgen05.commit releases stages)
-//   warp 11    TMEM allocator
+//   warp 11    TMEM allocator; in the peer CTA of a pair also the relay
 #include <stdlib.h>
 #include <mutex>
 #include "common.cuh"
@@ -46,6 +53,7 @@ constexpr uint32_t kSmemBudget = 220 * 1024;
 
 struct TcConfig {
   int T_acc;       // accumulators per pass (min(T, 4) timesteps for LIF, 1 for the T-summed linear read-out)
+  int pair;        // 1: 2-CTA clusters, tcgen05.mma.cta_group::2 (M = 256 per pair), half of every B block per CTA
   int n_tchunks;   // passes per tile: T / T_acc.  T = 8 / 16 run as 2 / 4 passes of 4 timesteps at N = 128 with the
                    // membrane potential carried between passes in an L2-resident fp32 plane, instead of one pass at
                    // N = 64 / 32 (whose A-operand fetch per MMA is amortised over too few columns)
@@ -143,6 +151,42 @@ __device__ __forceinline__ void tc_mma_f16_masked(uint32_t d_tmem, uint64_t ades
       "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
       : "memory");
 }
+// ---- cta_group::2 (two SMs of a cluster pair share one M = 256 MMA) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 remAddr32;\n\t"
+      "mapa.shared::cluster.u32  remAddr32, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64  _, [remAddr32];\n\t"
+      "}" ::"r"(bar), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_masked_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                       uint32_t accumulate, const uint32_t (&m)[8]) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8, %9, %10, %11, %12}, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]),
+      "r"(m[4]), "r"(m[5]), "r"(m[6]), "r"(m[7])
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -190,7 +234,10 @@ struct PipeState {
 // ---------------------------------------------------------------------------------------------------
 // NSPLIT = fp16 terms per weight, KSTEPS = KBLK / 16 (tcgen05.mma K = 16): compile-time so that the MMA issue loop
 // unrolls into descriptor-low-word additions with immediates.
-template <int NSPLIT, int KSTEPS>
+// PAIR: the CTA is one half of a 2-CTA cluster; the pair computes an M = 256 tile with tcgen05.mma.cta_group::2 issued by
+// the leader (rank 0).  Each SM stages its own 128 A rows and HALF of the B tile (N/2 rows), which cuts the
+// shared-memory operand fetch per MMA from A 4 KB + B 4 KB to A 4 KB + B 2 KB per SM.
+template <int NSPLIT, int KSTEPS, bool PAIR>
 __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcConfig& c = p.c;
@@ -204,28 +251,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
   auto acc_full = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages + s); };
   auto acc_empty = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages + 2 + s); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxAStages + 2 * kMaxBStages + 4));
+  // pair only: "the peer's stage has landed" barriers in the leader, arrived remotely by the peer's relay warp
+  auto a_full_peer = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages + 6 + s); };
+  auto b_full_peer = [&](int s) { return bar_base + 8u * (3 * kMaxAStages + 2 * kMaxBStages + 6 + s); };
   const uint32_t a_base = smem_u32(smem + 1024);
   const uint32_t b_base = a_base + c.a_stages * c.a_stage_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < c.a_stages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < c.b_stages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 8); }
+    for (int s = 0; s < c.a_stages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); mbar_init(a_full_peer(s), 1); }
+    for (int s = 0; s < c.b_stages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); mbar_init(b_full_peer(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), PAIR ? 16 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 11) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(512u));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(512u));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(512u));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = c.m_tiles * c.n_tiles;
+  // work units: (M tile, N tile) per CTA, or (pair of M tiles, N tile) per cluster
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int total_tiles = (PAIR ? (c.m_tiles + 1) / 2 : c.m_tiles) * c.n_tiles;
+  auto m_tile_of = [&](int unit) { return PAIR ? 2 * (unit / c.n_tiles) + (int)cta_rank : unit / c.n_tiles; };
   const int chunks = c.KBLK >> 3;            // 8-channel chunks per K block
   const uint32_t plane_bytes = (uint32_t)c.rows_ld * 16u;
 
@@ -233,8 +295,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     // ===== A producer =====
     PipeState st;
     const int ncopy = c.T_acc * chunks * c.ndx;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int64_t row0 = (int64_t)(tile / c.n_tiles) * kTileRows;
+    for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+      // an odd number of M tiles leaves the last pair with a phantom second tile: it re-reads the last real tile (its
+      // epilogue writes nothing because its rows are >= R_valid)
+      const int64_t row0 = (int64_t)min(m_tile_of(tile), c.m_tiles - 1) * kTileRows;
       for (int kbi = 0; kbi < c.num_kblocks * c.n_tchunks; ++kbi) {
         const int tch = kbi / c.num_kblocks, kb = kbi - tch * c.num_kblocks;
         if (lane == 0) {
@@ -261,47 +325,66 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     // ===== B producer (whole warp converged; one elected lane issues) =====
     PipeState st;
     const int64_t stage_halfs = c.b_stage_bytes / 2;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int halves = PAIR ? 2 : 1;                 // pair: each CTA stages its own half (N/2 rows) of every B block
+    for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
       const int n_tile = tile % c.n_tiles;
-      const __half* wsrc = p.wpack + (int64_t)n_tile * c.num_kblocks * 9 * stage_halfs;
+      const __half* wsrc = p.wpack + (int64_t)n_tile * c.num_kblocks * 9 * stage_halfs * halves + (int64_t)cta_rank * stage_halfs;
       for (int itt = 0; itt < c.num_kblocks * 9 * c.n_tchunks; ++itt) {
         const int it = itt % (c.num_kblocks * 9);      // every T pass streams the same weights again
         const int kb = it / 9, tap = tap_order(it - kb * 9);
         mbar_wait(b_empty(st.stage), st.phase ^ 1);
         if (elect_one()) {
           mbar_expect_tx(b_full(st.stage), c.b_stage_bytes);
-          bulk_g2s(b_base + st.stage * c.b_stage_bytes, wsrc + (int64_t)(kb * 9 + tap) * stage_halfs, c.b_stage_bytes,
-                   b_full(st.stage));
+          bulk_g2s(b_base + st.stage * c.b_stage_bytes, wsrc + (int64_t)(kb * 9 + tap) * stage_halfs * halves,
+                   c.b_stage_bytes, b_full(st.stage));
         }
         __syncwarp();
         st.advance(c.b_stages);
       }
     }
-  } else if (warp == 10) {
+  } else if (PAIR && warp == 11 && !leader) {
+    // ===== relay (peer CTA): tell the leader's MMA warp when this CTA's stages have landed, in consumption order =====
+    PipeState sa, sb;
+    for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+      for (int kbi = 0; kbi < c.num_kblocks * c.n_tchunks; ++kbi) {
+        mbar_wait(a_full(sa.stage), sa.phase);
+        if (lane == 0) mbar_arrive_remote(a_full_peer(sa.stage), 0);
+        __syncwarp();
+        for (int ti = 0; ti < 9; ++ti) {
+          mbar_wait(b_full(sb.stage), sb.phase);
+          if (lane == 0) mbar_arrive_remote(b_full_peer(sb.stage), 0);
+          __syncwarp();
+          sb.advance(c.b_stages);
+        }
+        sa.advance(c.a_stages);
+      }
+    }
+  } else if (warp == 10 && leader) {
     // ===== MMA issuer (whole warp converged; one elected lane issues tcgen05.mma / tcgen05.commit) =====
     PipeState sa, sb, sc;
     // descriptor words: lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version(1)<<14; all stepping is done on lo
     const uint32_t desc_hi = (128u >> 4) | (1u << 14);
     const uint32_t a_lo_const = (((uint32_t)c.ndx * plane_bytes) >> 4) << 16;   // LBO: next 8-channel chunk
-    const uint32_t b_lbo = (uint32_t)c.N_TILE * 16u;
+    const uint32_t b_lbo = (uint32_t)(PAIR ? c.N_TILE / 2 : c.N_TILE) * 16u;   // rows of B staged in THIS CTA
     const uint32_t b_lo_const = (b_lbo >> 4) << 16;
     const uint32_t a_step_t = ((uint32_t)(chunks * c.ndx) * plane_bytes) >> 4;
     const uint32_t a_step_k = ((uint32_t)(2 * c.ndx) * plane_bytes) >> 4;
     const uint32_t b_step_sp = ((uint32_t)chunks * b_lbo) >> 4;
     const uint32_t b_step_k = (2u * b_lbo) >> 4;
+    constexpr int MW = PAIR ? 8 : 4;   // 32-lane mask words: 128 output rows per CTA
     // one iteration per (tile, T pass)
-    for (int tile = blockIdx.x, tch = 0; tile < total_tiles;
-         (++tch == c.n_tchunks) ? (tch = 0, tile += gridDim.x) : 0) {
+    for (int tile = unit0, tch = 0; tile < total_tiles;
+         (++tch == c.n_tchunks) ? (tch = 0, tile += unit_stride) : 0) {
       mbar_wait(acc_empty(sc.stage), sc.phase ^ 1);
       tc_fence_after();
       const uint32_t d_base = tmem_base + (uint32_t)(sc.stage * c.T_acc * c.N_TILE);
       // rows of this tile on the top / bottom / left / right border of their image: the taps that would read across
       // that border have these output rows disabled
-      uint32_t m_up[4], m_dn[4], m_lf[4], m_rt[4];
+      uint32_t m_up[MW], m_dn[MW], m_lf[MW], m_rt[MW];
       {
-        const int64_t row0 = (int64_t)(tile / c.n_tiles) * kTileRows;
+        const int64_t row0 = (int64_t)m_tile_of(tile) * kTileRows;   // leader: first row of the pair
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
+        for (int w = 0; w < MW; ++w) {
           const int pp = (int)((row0 + w * 32 + lane) % p.P);
           const int y = pp / p.W, x = pp - y * p.W;
           m_up[w] = __ballot_sync(0xffffffffu, y == 0);
@@ -312,10 +395,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
       }
       for (int kb = 0; kb < c.num_kblocks; ++kb) {
         mbar_wait(a_full(sa.stage), sa.phase);
+        if (PAIR) mbar_wait(a_full_peer(sa.stage), sa.phase);
         const uint32_t a_stage = a_base + sa.stage * c.a_stage_bytes;
         for (int ti = 0; ti < 9; ++ti) {
           const int tap = tap_order(ti);
           mbar_wait(b_full(sb.stage), sb.phase);
+          if (PAIR) mbar_wait(b_full_peer(sb.stage), sb.phase);
           tc_fence_after();
           if (elect_one()) {
             const int dy = tap / 3 - 1, kx = tap % 3;
@@ -325,11 +410,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
             const uint32_t b_lo0 = b_lo_const | ((b_base + sb.stage * c.b_stage_bytes) >> 4);
             uint32_t d = d_base;
             const uint32_t first = (kb | ti) != 0 ? 1u : 0u;
-            uint32_t km[4];
+            uint32_t km[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-            for (int w = 0; w < 4; ++w)
+            for (int w = 0; w < MW; ++w)
               km[w] = (dy < 0 ? m_up[w] : (dy > 0 ? m_dn[w] : 0u)) | (kx == 0 ? m_lf[w] : (kx == 2 ? m_rt[w] : 0u));
-            const uint32_t k0 = km[0], k1 = km[1], k2 = km[2], k3 = km[3];
             for (int t = 0; t < c.T_acc; ++t) {
 #pragma unroll
               for (int sp = 0; sp < NSPLIT; ++sp) {
@@ -337,21 +421,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
                 for (int ks = 0; ks < KSTEPS; ++ks) {
                   const uint64_t adesc = ((uint64_t)desc_hi << 32) | (a_lo + ks * a_step_k);
                   const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (b_lo0 + sp * b_step_sp + ks * b_step_k);
-                  tc_mma_f16_masked(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first, k0, k1, k2, k3);
+                  if (PAIR) tc_mma_f16_masked_pair(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first, km);
+                  else tc_mma_f16_masked(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first, km[0], km[1], km[2], km[3]);
                 }
               }
               a_lo += a_step_t;
               d += (uint32_t)c.N_TILE;
             }
-            tc_commit(b_empty(sb.stage));
-            if (ti == 8) tc_commit(a_empty(sa.stage));
+            if (PAIR) { tc_commit_pair(b_empty(sb.stage)); if (ti == 8) tc_commit_pair(a_empty(sa.stage)); }
+            else { tc_commit(b_empty(sb.stage)); if (ti == 8) tc_commit(a_empty(sa.stage)); }
           }
           __syncwarp();
           sb.advance(c.b_stages);
         }
         sa.advance(c.a_stages);
       }
-      if (elect_one()) tc_commit(acc_full(sc.stage));
+      if (elect_one()) { if (PAIR) tc_commit_pair(acc_full(sc.stage)); else tc_commit(acc_full(sc.stage)); }
       __syncwarp();
       sc.advance(c.acc_stages);
     }
@@ -367,11 +452,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     const bool tau_pow2 = frexpf(p.tau, &tau_exp) == 0.5f;
     const float inv_tau = 1.0f / p.tau;
     const bool fast_lif = tau_pow2 && p.hard_reset && p.v_reset == 0.f;
-    for (int tile = blockIdx.x, tch = 0; tile < total_tiles;
-         (++tch == c.n_tchunks) ? (tch = 0, tile += gridDim.x) : 0) {
+    for (int tile = unit0, tch = 0; tile < total_tiles;
+         (++tch == c.n_tchunks) ? (tch = 0, tile += unit_stride) : 0) {
       const bool first_pass = tch == 0, last_pass = tch == c.n_tchunks - 1;
       const int n0 = (tile % c.n_tiles) * c.N_TILE;
-      const int64_t r = (int64_t)(tile / c.n_tiles) * kTileRows + q * 32 + lane;  // row (without guard)
+      const int64_t r = (int64_t)m_tile_of(tile) * kTileRows + q * 32 + lane;  // row (without guard)
       const int pp = (int)(r % p.P);
       const int py = pp / p.W, px = pp - py * p.W;
       const bool valid = r < p.R_valid;
@@ -500,16 +585,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty(sc.stage));
+      if (lane == 0) { if (PAIR && !leader) mbar_arrive_remote(acc_empty(sc.stage), 0); else mbar_arrive(acc_empty(sc.stage)); }
       sc.advance(c.acc_stages);
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 11) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
 }
 
@@ -582,6 +668,11 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
     return SD_ERR_UNSUPPORTED;
   }
   c->N_TILE = n_tile;
+  {
+    const int64_t rows = (int64_t)d->B * d->H_in * d->W_in;
+    const int m_tiles = (int)((rows + kTileRows - 1) / kTileRows);
+    c->pair = (env_int("SD_TC_PAIR", 1) && n_tile == 128 && m_tiles >= 2) ? 1 : 0;
+  }
   c->acc_stages = 512 / (c->T_acc * n_tile) >= 2 ? 2 : 1;
   c->acc_stages = env_int("SD_TC_ACC_STAGES", c->acc_stages) >= 2 && 512 / (c->T_acc * n_tile) >= 2 ? 2 : 1;
   const int c0 = d->C_in0, c1 = d->C_in - d->C_in0;
@@ -601,7 +692,7 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
       if (kblk_pref && kblk != kblk_pref) continue;   // default: the largest K block that leaves >= 2 A + 4 B stages
       if (c0 % kblk || c1 % kblk) continue;
       c->a_stage_bytes = (uint32_t)c->T_acc * (kblk / 8) * ndx * c->rows_ld * 16;
-      c->b_stage_bytes = (uint32_t)d->nsplit * (kblk / 8) * n_tile * 16;
+      c->b_stage_bytes = (uint32_t)d->nsplit * (kblk / 8) * (c->pair ? n_tile / 2 : n_tile) * 16;   // per CTA
       // The K block fixes the fp32 accumulation order ((channel block, tap, 16-channel step)), so it must not depend
       // on the batch size: the fit test uses the N = 128 stage size even when a small batch runs narrower tiles.
       // A batch shard then reproduces the unsharded result bit for bit.
@@ -654,20 +745,24 @@ __global__ void tc_chan_exp_kernel(const float* __restrict__ w, int Cin, float* 
   }
 }
 
+// layout [n_tile][k_block][tap][half][split][chunk][n (N_TILE / halves)][8]; halves = 2 for the cta_group::2 variant
 __global__ void tc_pack_kernel(const float* __restrict__ w, const int* __restrict__ e_in, __half* __restrict__ out,
-                               int Cout, int Cin, int N_TILE, int KBLK, int nsplit, int n_tiles, int num_kblocks) {
+                               int Cout, int Cin, int N_TILE, int KBLK, int nsplit, int n_tiles, int num_kblocks,
+                               int halves) {
   const int chunks = KBLK / 8;
+  const int NH = N_TILE / halves;
   const int64_t total = (int64_t)n_tiles * num_kblocks * 9 * nsplit * chunks * N_TILE * 8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int j = (int)(i % 8);
     int64_t r = i / 8;
-    int n = (int)(r % N_TILE); r /= N_TILE;
+    int n = (int)(r % NH); r /= NH;
     int ch = (int)(r % chunks); r /= chunks;
     int sp = (int)(r % nsplit); r /= nsplit;
+    int hf = (int)(r % halves); r /= halves;
     int tap = (int)(r % 9); r /= 9;
     int kb = (int)(r % num_kblocks);
     int nt = (int)(r / num_kblocks);
-    const int co = nt * N_TILE + n;
+    const int co = nt * N_TILE + hf * NH + n;
     const int ci = kb * KBLK + ch * 8 + j;
     float val = 0.f;
     if (co < Cout) {
@@ -705,7 +800,7 @@ int64_t sd_conv_weight_bytes_tc(const sd_conv_desc* d) {
   TcConfig c;
   if (!d || validate_conv_desc(d) != SD_OK || tc_config(d, &c) != SD_OK) return 0;
   // + C_out ints of scratch for the per-channel exponents at the end
-  return (int64_t)c.n_tiles * c.num_kblocks * 9 * c.b_stage_bytes + (int64_t)d->C_out * 4;
+  return (int64_t)c.n_tiles * c.num_kblocks * 9 * c.b_stage_bytes * (c.pair ? 2 : 1) + (int64_t)d->C_out * 4;
 }
 
 int sd_conv_pack_weights_tc(const sd_conv_desc* d, const float* w, void* packed, float* chan_scale_out, void* stream) {
@@ -717,7 +812,7 @@ int sd_conv_pack_weights_tc(const sd_conv_desc* d, const float* w, void* packed,
   SD_REQUIRE(w && packed && chan_scale_out, "null pointer argument");
   SD_DEVICE_OR_RETURN();
   cudaStream_t st = as_stream(stream);
-  const int64_t main_bytes = (int64_t)c.n_tiles * c.num_kblocks * 9 * c.b_stage_bytes;
+  const int64_t main_bytes = (int64_t)c.n_tiles * c.num_kblocks * 9 * c.b_stage_bytes * (c.pair ? 2 : 1);
   int* e_buf = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(packed) + main_bytes);
   tc_chan_exp_kernel<<<d->C_out, 256, 0, st>>>(w, d->C_in, chan_scale_out, e_buf);
   SD_LAUNCH_CHECK();
@@ -725,7 +820,7 @@ int sd_conv_pack_weights_tc(const sd_conv_desc* d, const float* w, void* packed,
   int64_t blocks = (total + 255) / 256;
   if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
   tc_pack_kernel<<<(unsigned)blocks, 256, 0, st>>>(w, e_buf, (__half*)packed, d->C_out, d->C_in, c.N_TILE, c.KBLK,
-                                                   d->nsplit, c.n_tiles, c.num_kblocks);
+                                                   d->nsplit, c.n_tiles, c.num_kblocks, c.pair ? 2 : 1);
   SD_LAUNCH_CHECK();
   return SD_OK;
 }
@@ -767,21 +862,44 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
   p.nsplit = d->nsplit; p.out_kind = d->out_kind; p.hard_reset = d->hard_reset;
   p.tau = d->tau; p.v_th = d->v_threshold; p.v_reset = d->v_reset;
   // cute::UMMA::InstrDescriptor: c_format F32 (bit 4), a/b F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-  p.idesc = (1u << 4) | ((uint32_t)(c.N_TILE >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
+  p.idesc = (1u << 4) | ((uint32_t)(c.N_TILE >> 3) << 17) | ((uint32_t)((c.pair ? 2 * kTileRows : kTileRows) >> 4) << 24);
   p.c = c;
-  int grid = c.m_tiles * c.n_tiles;
-  if (grid > sm_count()) grid = sm_count();
   cudaStream_t st = as_stream(stream);
-#define SD_TC_LAUNCH(NS, KS)                                                                                       \
+  int grid;
+  if (c.pair) {
+    const int units = ((c.m_tiles + 1) / 2) * c.n_tiles;
+    grid = 2 * (units < sm_count() / 2 ? units : sm_count() / 2);
+  } else {
+    grid = c.m_tiles * c.n_tiles;
+    if (grid > sm_count()) grid = sm_count();
+  }
+#define SD_TC_LAUNCH_ONE(NS, KS, PR)                                                                               \
   do {                                                                                                             \
     static std::once_flag once;                                                                                    \
     static cudaError_t attr_rc = cudaSuccess;                                                                      \
     std::call_once(once, [] {                                                                                      \
-      attr_rc = cudaFuncSetAttribute(conv3x3_tc_kernel<NS, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+      attr_rc = cudaFuncSetAttribute(conv3x3_tc_kernel<NS, KS, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                      227 * 1024);                                                                  \
     });                                                                                                            \
     SD_CUDA(attr_rc);                                                                                              \
-    conv3x3_tc_kernel<NS, KS><<<grid, kTcThreads, c.smem_bytes, st>>>(p);                                          \
+    cudaLaunchConfig_t cfg = {};                                                                                   \
+    cfg.gridDim = dim3((unsigned)grid);                                                                            \
+    cfg.blockDim = dim3(kTcThreads);                                                                               \
+    cfg.dynamicSmemBytes = c.smem_bytes;                                                                           \
+    cfg.stream = st;                                                                                               \
+    cudaLaunchAttribute attr[1];                                                                                   \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                                              \
+    attr[0].val.clusterDim.x = PR ? 2 : 1;                                                                         \
+    attr[0].val.clusterDim.y = 1;                                                                                  \
+    attr[0].val.clusterDim.z = 1;                                                                                  \
+    cfg.attrs = attr;                                                                                              \
+    cfg.numAttrs = 1;                                                                                              \
+    SD_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<NS, KS, PR>, p));                                           \
+  } while (0)
+#define SD_TC_LAUNCH(NS, KS)                                    \
+  do {                                                          \
+    if (c.pair) SD_TC_LAUNCH_ONE(NS, KS, true);                 \
+    else SD_TC_LAUNCH_ONE(NS, KS, false);                       \
   } while (0)
   const int ks = c.KBLK / 16;
   if (d->nsplit == 1) {
@@ -790,6 +908,7 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
     if (ks == 1) SD_TC_LAUNCH(2, 1); else if (ks == 2) SD_TC_LAUNCH(2, 2); else SD_TC_LAUNCH(2, 4);
   }
 #undef SD_TC_LAUNCH
+#undef SD_TC_LAUNCH_ONE
   SD_LAUNCH_CHECK();
   return SD_OK;
 }

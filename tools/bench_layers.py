@@ -13,10 +13,7 @@ from spiking_diffusion_b200 import engine  # noqa: E402
 
 CONFIGS = [
     {},
-    {"SD_TC_TACC": "2"},
-    {"SD_TC_TACC": "2", "SD_TC_N256": "1"},
-    {"SD_TC_TACC": "1", "SD_TC_N256": "1"},
-    {"SD_TC_TACC": "2", "SD_TC_KBLK": "64"},
+    {"SD_TC_PAIR": "1"},
 ]
 
 
