@@ -335,11 +335,15 @@ def main():
     ap.add_argument("--nsplit", type=int, default=2, choices=[1, 2])
     ap.add_argument("--cpu-batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=0, help="experiment: override the workload's per-GPU batch")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch > 0:
+        wl["desc"] = wl["desc"].replace(f"b={wl['b']}", f"b={args.batch} (overridden)")
+        wl["b"] = args.batch
     if args.impl == "reference":
         run_reference(args, wl, rank, world)
         return

@@ -157,6 +157,9 @@ typedef struct sd_conv_desc {
   float tau, v_threshold, v_reset;
   int hard_reset;        /* LIFNode(v_reset=None) <=> 0 */
   int nsplit;            /* tc only: fp16 terms per fp32 weight (1 or 2), see sd_conv_pack_weights_tc */
+  int concurrent;        /* tc only, tuning hint: how many launches of this size the caller keeps in flight on
+                            different streams (0 or 1 = this launch has the GPU to itself).  A lone small batch is
+                            cut into narrower N tiles to occupy more SMs; concurrent sub-batches are not. */
 } sd_conv_desc;
 
 typedef struct sd_conv_args {
@@ -177,6 +180,10 @@ typedef struct sd_conv_args {
 int64_t sd_conv_weight_bytes_simt(const sd_conv_desc* d);
 int64_t sd_conv_weight_bytes_tc(const sd_conv_desc* d);
 int64_t sd_conv_workspace_bytes(const sd_conv_desc* d);
+/* Key of the packed tc weight layout (N tile, K block, CTA pairing).  The layout depends on the batch size through the
+ * tile configuration: descriptors that differ only in B / concurrent may share one packed buffer iff their keys are
+ * equal.  Returns -1 for unsupported descriptors. */
+int64_t sd_conv_weight_layout_tc(const sd_conv_desc* d);
 /* w: the reference's own parameter layout, fp32 [C_out, C_in, kh, kw] (Conv2d) or [C_in, C_out, kh, kw]
  * (ConvTranspose2d).  tc packing splits each weight into nsplit fp16 terms after an exact power-of-two
  * per-output-channel scaling; chan_scale_out [C_out] receives the inverse scaling to be multiplied
@@ -188,6 +195,10 @@ int sd_conv_lif_simt(const sd_conv_desc* d, const sd_conv_args* a, void* stream)
 int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream);
 /* 1 if sd_conv_lif_tc supports the descriptor on this build. */
 int sd_conv_tc_supported(const sd_conv_desc* d);
+/* Diagnostics (tools/trace_tc.py): while `buf` (device memory, >= grid * 64 int64) is set, sd_conv_lif_tc launches
+ * write per-CTA cycle stamps of the MMA and epilogue warps to it.  Pass NULL to switch tracing off.  No reference
+ * counterpart. */
+int sd_debug_tc_trace(void* buf);
 
 /* ---- (f.1) training-path kernels (first correct versions, CUDA cores) ------------------------------------------
  * The reference trains through torch autograd over F.conv2d / F.conv_transpose2d / F.batch_norm

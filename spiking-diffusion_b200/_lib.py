@@ -24,8 +24,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 SYMBOLS = [
     "sd_last_error", "sd_version", "sd_device_info", "sd_stf_guard", "sd_stf_rows", "sd_stf_bytes",
     "sd_stf_from_nchw", "sd_stf_to_nchw", "sd_channel_affine", "sd_state_convert", "sd_lif_forward", "sd_lif_backward", "sd_memout", "sd_vq_feature", "sd_vq_lookup",
-    "sd_vq_gather", "sd_conv_weight_bytes_simt", "sd_conv_weight_bytes_tc", "sd_conv_workspace_bytes", "sd_conv_pack_weights_simt",
-    "sd_conv_pack_weights_tc", "sd_conv_lif_simt", "sd_conv_lif_tc", "sd_conv_tc_supported", "sd_conv_wgrad",
+    "sd_vq_gather", "sd_conv_weight_bytes_simt", "sd_conv_weight_bytes_tc", "sd_conv_workspace_bytes", "sd_conv_weight_layout_tc", "sd_conv_pack_weights_simt",
+    "sd_conv_pack_weights_tc", "sd_conv_lif_simt", "sd_conv_lif_tc", "sd_conv_tc_supported", "sd_debug_tc_trace", "sd_conv_wgrad",
     "sd_bn_train_forward", "sd_bn_backward", "sd_philox_uniform",
     "sd_philox_exponential", "sd_philox_offset_increment", "sd_sample_step", "sd_sample_step_dev", "sd_denoiser_input", "sd_to_uint8",
 ]
@@ -80,7 +80,7 @@ class ConvDesc(ctypes.Structure):
                 ("T", "B", "C_in", "H_in", "W_in", "C_out", "H_out", "W_out", "kh", "kw", "stride", "pad",
                  "transposed", "in_kind", "out_kind", "in_T", "C_in0")] + \
                [("tau", ctypes.c_float), ("v_threshold", ctypes.c_float), ("v_reset", ctypes.c_float),
-                ("hard_reset", ctypes.c_int), ("nsplit", ctypes.c_int)]
+                ("hard_reset", ctypes.c_int), ("nsplit", ctypes.c_int), ("concurrent", ctypes.c_int)]
 
 
 class ConvArgs(ctypes.Structure):
@@ -121,11 +121,13 @@ def _declare(lib: ctypes.CDLL) -> None:
         "sd_conv_weight_bytes_simt": (i64, [pd]),
         "sd_conv_weight_bytes_tc": (i64, [pd]),
         "sd_conv_workspace_bytes": (i64, [pd]),
+        "sd_conv_weight_layout_tc": (i64, [pd]),
         "sd_conv_pack_weights_simt": (i, [pd, vp, vp, vp]),
         "sd_conv_pack_weights_tc": (i, [pd, vp, vp, vp, vp]),
         "sd_conv_lif_simt": (i, [pd, pa, vp]),
         "sd_conv_lif_tc": (i, [pd, pa, vp]),
         "sd_conv_tc_supported": (i, [pd]),
+        "sd_debug_tc_trace": (i, [vp]),
         "sd_conv_wgrad": (i, [pd, vp, vp, vp, vp, vp]),
         "sd_bn_train_forward": (i, [vp, vp, vp, vp, vp, vp, i64, i, i64, f, vp]),
         "sd_bn_backward": (i, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i, i64, f, vp]),

@@ -43,6 +43,7 @@
 #include <stdlib.h>
 #include <mutex>
 #include "common.cuh"
+#include <type_traits>
 
 namespace sd {
 
@@ -87,8 +88,11 @@ struct TcParams {
   int nsplit, out_kind, hard_reset;
   float tau, v_th, v_reset;
   uint32_t idesc;
+  long long* trace;         // diagnostics (sd_debug_tc_trace): per-CTA cycle stamps, or null
+  int dbg;                  // diagnostics (env SD_TC_DBG): 1 = skip the spike stores, 2 = skip the TMEM loads
   TcConfig c;
 };
+constexpr int kTraceStride = 64;   // int64 slots per CTA: [0] entry, [1] set-up done, [2] exit, then 8 per tile pass
 
 // ---------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -195,6 +199,14 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld that also names the destination registers as in/out operands, so no use of them can be scheduled above it
+__device__ __forceinline__ void tc_ld_wait_on(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 
 // Shared-memory matrix descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor field layout):
 //   [0,14) start >> 4 | [16,30) LBO >> 4 | [32,46) SBO >> 4 | [46,48) version = 1 | [61,64) layout = 0 (none)
@@ -260,6 +272,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
+  long long* trace = p.trace ? p.trace + (int64_t)blockIdx.x * kTraceStride : nullptr;
+  if (trace && threadIdx.x == 0) trace[0] = clock64();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < c.a_stages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); mbar_init(a_full_peer(s), 1); }
@@ -282,6 +296,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
   if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (trace && threadIdx.x == 0) trace[1] = clock64();
 
   // work units: (M tile, N tile) per CTA, or (pair of M tiles, N tile) per cluster
   const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -373,19 +388,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     const uint32_t b_step_k = (2u * b_lbo) >> 4;
     constexpr int MW = PAIR ? 8 : 4;   // 32-lane mask words: 128 output rows per CTA
     // one iteration per (tile, T pass)
+    int trace_it = 0;
     for (int tile = unit0, tch = 0; tile < total_tiles;
          (++tch == c.n_tchunks) ? (tch = 0, tile += unit_stride) : 0) {
-      mbar_wait(acc_empty(sc.stage), sc.phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_base = tmem_base + (uint32_t)(sc.stage * c.T_acc * c.N_TILE);
+      long long stall = 0;
       // rows of this tile on the top / bottom / left / right border of their image: the taps that would read across
-      // that border have these output rows disabled
+      // that border have these output rows disabled.  Computed before the accumulator wait, so it overlaps the
+      // epilogue of the previous tile.
       uint32_t m_up[MW], m_dn[MW], m_lf[MW], m_rt[MW];
       {
         const int64_t row0 = (int64_t)m_tile_of(tile) * kTileRows;   // leader: first row of the pair
+        const int pp0 = (int)(row0 % p.P);
 #pragma unroll
         for (int w = 0; w < MW; ++w) {
-          const int pp = (int)((row0 + w * 32 + lane) % p.P);
+          const int pp = (pp0 + w * 32 + lane) % p.P;
           const int y = pp / p.W, x = pp - y * p.W;
           m_up[w] = __ballot_sync(0xffffffffu, y == 0);
           m_dn[w] = __ballot_sync(0xffffffffu, y == p.H - 1);
@@ -393,14 +409,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
           m_rt[w] = __ballot_sync(0xffffffffu, x == p.W - 1);
         }
       }
+      mbar_wait(acc_empty(sc.stage), sc.phase ^ 1);
+      tc_fence_after();
+      if (trace && lane == 0 && trace_it < 7) trace[3 + trace_it * 8 + 0] = clock64();
+      const uint32_t d_base = tmem_base + (uint32_t)(sc.stage * c.T_acc * c.N_TILE);
       for (int kb = 0; kb < c.num_kblocks; ++kb) {
+        const long long w0 = trace ? clock64() : 0;
         mbar_wait(a_full(sa.stage), sa.phase);
         if (PAIR) mbar_wait(a_full_peer(sa.stage), sa.phase);
+        if (trace) stall += clock64() - w0;
         const uint32_t a_stage = a_base + sa.stage * c.a_stage_bytes;
         for (int ti = 0; ti < 9; ++ti) {
           const int tap = tap_order(ti);
+          const long long w1 = trace ? clock64() : 0;
           mbar_wait(b_full(sb.stage), sb.phase);
           if (PAIR) mbar_wait(b_full_peer(sb.stage), sb.phase);
+          if (trace) {
+            stall += clock64() - w1;
+            if (kb == 0 && ti == 0 && lane == 0 && trace_it < 7) trace[3 + trace_it * 8 + 1] = clock64();
+          }
           tc_fence_after();
           if (elect_one()) {
             const int dy = tap / 3 - 1, kx = tap % 3;
@@ -438,6 +465,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
       }
       if (elect_one()) { if (PAIR) tc_commit_pair(acc_full(sc.stage)); else tc_commit(acc_full(sc.stage)); }
       __syncwarp();
+      if (trace && lane == 0 && trace_it < 7) {
+        trace[3 + trace_it * 8 + 2] = clock64();
+        trace[3 + trace_it * 8 + 3] = stall;
+      }
+      ++trace_it;
       sc.advance(c.acc_stages);
     }
   } else if (warp < 8) {
@@ -452,6 +484,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     const bool tau_pow2 = frexpf(p.tau, &tau_exp) == 0.5f;
     const float inv_tau = 1.0f / p.tau;
     const bool fast_lif = tau_pow2 && p.hard_reset && p.v_reset == 0.f;
+    int trace_it = 0;
     for (int tile = unit0, tch = 0; tile < total_tiles;
          (++tch == c.n_tchunks) ? (tch = 0, tile += unit_stride) : 0) {
       const bool first_pass = tch == 0, last_pass = tch == c.n_tchunks - 1;
@@ -462,6 +495,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
       const bool valid = r < p.R_valid;
       mbar_wait(acc_full(sc.stage), sc.phase);
       tc_fence_after();
+      if (trace && threadIdx.x == 0 && trace_it < 7) trace[3 + trace_it * 8 + 4] = clock64();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc.stage * c.T_acc * c.N_TILE);
       for (int cc = col_lo; cc < col_hi; cc += 16) {
         const int n = n0 + cc;  // first output channel of this 16-column group (warp-uniform)
@@ -475,7 +509,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
           sh_[j] = b.x; sh_[j + 1] = b.y; sh_[j + 2] = b.z; sh_[j + 3] = b.w;
         }
         if (p.out_kind == SD_OUT_LIF) {
-          float v[16], cnt[16];
+          float v[16];
+          __half2 cnt2[8];   // spike counts so far (exact in fp16: at most T <= 16)
+          const bool want_sum = p.out_sum != nullptr;
           const int64_t vrow = ((int64_t)(n >> 3) * p.R_alloc + p.G + r) * 8;  // chunk n/8; next chunk + R_alloc*8
           if (p.v != nullptr && valid && n < p.Cout && (!first_pass || p.v_load_initial)) {
 #pragma unroll
@@ -490,65 +526,74 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
             for (int j = 0; j < 16; ++j) v[j] = p.hard_reset ? p.v_reset : 0.f;
           }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) cnt[j] = 0.f;
-          if (!first_pass && p.out_sum != nullptr && valid) {   // spike counts of the earlier passes
+          for (int k = 0; k < 8; ++k) cnt2[k] = __floats2half2_rn(0.f, 0.f);
+          if (!first_pass && want_sum && valid) {   // spike counts of the earlier passes
             const __half* o = p.out_sum + ((int64_t)(n >> 3) * p.R_alloc + p.G + r) * 8;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const uint4 raw = *reinterpret_cast<const uint4*>(o + (int64_t)h * p.R_alloc * 8);
               const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 f = __half22float2(h2[k]);
-                cnt[8 * h + 2 * k] = f.x; cnt[8 * h + 2 * k + 1] = f.y;
-              }
+              for (int k = 0; k < 4; ++k) cnt2[4 * h + k] = h2[k];
             }
           }
-          for (int tl = 0; tl < c.T_acc; ++tl) {
-            const int t = tch * c.T_acc + tl;
-            uint32_t acc[16];
-            tc_ld16(t_base + (uint32_t)(tl * c.N_TILE + cc), acc);
-            tc_ld_wait();
+          // one timestep of 16 columns: BN affine, charge, fire, reset; spikes leave as packed fp16
+          auto lif_step = [&](auto fast_tag, const uint32_t (&acc)[16], int tl) {
+            constexpr bool kFast = decltype(fast_tag)::value;
             uint32_t packed[8];
-            if (fast_lif) {
-              // hard reset to 0, tau a power of two: h = v + (x - v) * (1/tau) is one exact-product FMA
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float x = fmaf(__uint_as_float(acc[j]), sc_[j], sh_[j]);
-                const float h = fmaf(__fsub_rn(x, v[j]), inv_tau, v[j]);
-                const bool s = h >= p.v_th;
-                v[j] = s ? 0.f : h;
-                cnt[j] += s ? 1.f : 0.f;
-                const uint32_t bits = s ? 0x3C00u : 0u;  // fp16 1.0
-                if (j & 1) packed[j >> 1] |= bits << 16; else packed[j >> 1] = bits;
-              }
-            } else {
+            for (int j = 0; j < 16; j += 2) {
+              float sf[2];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float x = fmaf(__uint_as_float(acc[j]), sc_[j], sh_[j]);
-                const float dv = p.hard_reset ? __fsub_rn(x, __fsub_rn(v[j], p.v_reset)) : __fsub_rn(x, v[j]);
-                const float h = __fadd_rn(v[j], tau_pow2 ? __fmul_rn(dv, inv_tau) : __fdiv_rn(dv, p.tau));
-                const bool s = h >= p.v_th;
-                v[j] = p.hard_reset ? (s ? p.v_reset : h) : (s ? __fsub_rn(h, p.v_th) : h);
-                cnt[j] += s ? 1.f : 0.f;
-                const uint32_t bits = s ? 0x3C00u : 0u;  // fp16 1.0
-                if (j & 1) packed[j >> 1] |= bits << 16; else packed[j >> 1] = bits;
+              for (int u = 0; u < 2; ++u) {
+                const float x = fmaf(__uint_as_float(acc[j + u]), sc_[j + u], sh_[j + u]);
+                if constexpr (kFast) {
+                  // hard reset to 0, tau a power of two: h = v + (x - v) * (1/tau) is one exact-product FMA, and
+                  // v' = h - h * s is exactly (s ? 0 : h)
+                  const float h = fmaf(__fsub_rn(x, v[j + u]), inv_tau, v[j + u]);
+                  sf[u] = h >= p.v_th ? 1.f : 0.f;
+                  v[j + u] = fmaf(-h, sf[u], h);
+                } else {
+                  const float dv = p.hard_reset ? __fsub_rn(x, __fsub_rn(v[j + u], p.v_reset)) : __fsub_rn(x, v[j + u]);
+                  const float h = __fadd_rn(v[j + u], tau_pow2 ? __fmul_rn(dv, inv_tau) : __fdiv_rn(dv, p.tau));
+                  const bool s = h >= p.v_th;
+                  sf[u] = s ? 1.f : 0.f;
+                  v[j + u] = p.hard_reset ? (s ? p.v_reset : h) : (s ? __fsub_rn(h, p.v_th) : h);
+                }
               }
+              const __half2 s2 = __floats2half2_rn(sf[0], sf[1]);
+              packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&s2);
+              if (want_sum) cnt2[j >> 1] = __hadd2(cnt2[j >> 1], s2);
             }
-            if (valid && n < p.Cout && p.out_spk != nullptr) {
+            if (valid && n < p.Cout && p.out_spk != nullptr && !(p.dbg & 1)) {
+              const int t = tch * c.T_acc + tl;
               __half* o = p.out_spk + (((int64_t)t * p.Cout8 + (n >> 3)) * p.R_alloc + p.G + r) * 8;
               *reinterpret_cast<uint4*>(o) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
               *reinterpret_cast<uint4*>(o + p.R_alloc * 8) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
             }
-          }
-          if (valid && n < p.Cout) {
-            if (p.out_sum != nullptr) {
-              uint32_t pk[8];
+          };
+          // two register sets: the TMEM load of timestep t + 1 is in flight while timestep t is computed
+          auto lif_all = [&](auto fast_tag) {
+            uint32_t accA[16], accB[16];
+            const bool ld = !(p.dbg & 2);
 #pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                const __half2 h2 = __floats2half2_rn(cnt[j], cnt[j + 1]);
-                pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+            for (int j = 0; j < 16; ++j) accA[j] = accB[j] = 0u;
+            if (ld) tc_ld16(t_base + (uint32_t)cc, accA);
+            for (int tl = 0; tl < c.T_acc; tl += 2) {
+              tc_ld_wait_on(accA);
+              if (tl + 1 < c.T_acc && ld) tc_ld16(t_base + (uint32_t)((tl + 1) * c.N_TILE + cc), accB);
+              lif_step(fast_tag, accA, tl);
+              if (tl + 1 < c.T_acc) {
+                tc_ld_wait_on(accB);
+                if (tl + 2 < c.T_acc && ld) tc_ld16(t_base + (uint32_t)((tl + 2) * c.N_TILE + cc), accA);
+                lif_step(fast_tag, accB, tl + 1);
               }
+            }
+          };
+          if (fast_lif) lif_all(std::true_type{}); else lif_all(std::false_type{});
+          if (valid && n < p.Cout) {
+            if (want_sum) {
+              const uint32_t* pk = reinterpret_cast<const uint32_t*>(cnt2);
               __half* o = p.out_sum + ((int64_t)(n >> 3) * p.R_alloc + p.G + r) * 8;
               *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               *reinterpret_cast<uint4*>(o + p.R_alloc * 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -586,12 +631,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { if (PAIR && !leader) mbar_arrive_remote(acc_empty(sc.stage), 0); else mbar_arrive(acc_empty(sc.stage)); }
+      if (trace && threadIdx.x == 0 && trace_it < 7) trace[3 + trace_it * 8 + 5] = clock64();
+      ++trace_it;
       sc.advance(c.acc_stages);
     }
   }
 
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (trace && threadIdx.x == 0) trace[2] = clock64();
   if (warp == 11) {
     tc_fence_after();
     if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
@@ -657,8 +705,9 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
     const int sms = sm_count() > 0 ? sm_count() : 148;
     const int64_t rows = (int64_t)d->B * d->H_in * d->W_in;
     const int m_tiles = (int)((rows + kTileRows - 1) / kTileRows);
+    const int conc = d->concurrent > 1 ? d->concurrent : 1;   // sub-batches on other streams fill the SMs instead
     while (n_tile > 32 && env_int("SD_TC_SMALL_BATCH_SPLIT", 1) &&
-           (int64_t)m_tiles * ((d->C_out + n_tile - 1) / n_tile) * 2 <= sms && d->C_out > n_tile / 2)
+           (int64_t)m_tiles * ((d->C_out + n_tile - 1) / n_tile) * 2 * conc <= sms && d->C_out > n_tile / 2)
       n_tile /= 2;
   }
   n_tile = env_int("SD_TC_NTILE", n_tile);
@@ -778,7 +827,18 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, const int* __restric
 
 using namespace sd;
 
+static long long* g_tc_trace = nullptr;   // diagnostics only (tools/trace_tc.py); not thread-safe by design
+
 extern "C" {
+
+// Diagnostics: the next sd_conv_lif_tc launches write per-CTA cycle stamps to `buf` (device memory, at least
+// grid * 64 int64; pass null to switch tracing off).  Layout per CTA: [0] entry, [1] set-up done, [2] exit, then per
+// tile pass i < 7 at 3 + 8 i: MMA warp got the accumulator, first operands landed, last MMA issued, cycles the MMA warp
+// waited for operands, epilogue saw the accumulator, epilogue released it.
+int sd_debug_tc_trace(void* buf) {
+  g_tc_trace = (long long*)buf;
+  return SD_OK;
+}
 
 int sd_conv_tc_supported(const sd_conv_desc* d) {
   if (!d || validate_conv_desc(d) != SD_OK) return 0;
@@ -794,6 +854,12 @@ int64_t sd_conv_workspace_bytes(const sd_conv_desc* d) {
   if (c.n_tchunks <= 1) return 0;
   // one fp32 state plane [C_out/8][R_alloc][8]
   return (int64_t)c8(d->C_out) * stf_rows(d->B, d->H_out, d->W_out) * 8 * (int64_t)sizeof(float);
+}
+
+int64_t sd_conv_weight_layout_tc(const sd_conv_desc* d) {
+  TcConfig c;
+  if (!d || validate_conv_desc(d) != SD_OK || tc_config(d, &c) != SD_OK) return -1;
+  return ((int64_t)c.N_TILE << 16) | ((int64_t)c.KBLK << 4) | (int64_t)c.pair;
 }
 
 int64_t sd_conv_weight_bytes_tc(const sd_conv_desc* d) {
@@ -864,14 +930,17 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
   // cute::UMMA::InstrDescriptor: c_format F32 (bit 4), a/b F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
   p.idesc = (1u << 4) | ((uint32_t)(c.N_TILE >> 3) << 17) | ((uint32_t)((c.pair ? 2 * kTileRows : kTileRows) >> 4) << 24);
   p.c = c;
+  p.trace = g_tc_trace;
+  p.dbg = g_tc_trace ? env_int("SD_TC_DBG", 0) : 0;
   cudaStream_t st = as_stream(stream);
   int grid;
+  const bool persist = env_int("SD_TC_PERSIST", 1) != 0;   // experiment knob: 0 = one work unit per CTA / cluster
   if (c.pair) {
     const int units = ((c.m_tiles + 1) / 2) * c.n_tiles;
-    grid = 2 * (units < sm_count() / 2 ? units : sm_count() / 2);
+    grid = 2 * (units < sm_count() / 2 || !persist ? units : sm_count() / 2);
   } else {
     grid = c.m_tiles * c.n_tiles;
-    if (grid > sm_count()) grid = sm_count();
+    if (grid > sm_count() && persist) grid = sm_count();
   }
 #define SD_TC_LAUNCH_ONE(NS, KS, PR)                                                                               \
   do {                                                                                                             \

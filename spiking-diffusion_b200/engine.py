@@ -67,7 +67,8 @@ class FusedLayer:
 
     def __init__(self, conv, bn, lif, *, T: int, B: int, H_in: int, W_in: int, in_kind: int, out_kind: int,
                  impl: str = "auto", nsplit: int = 2, in_T: Optional[int] = None, C_in0: Optional[int] = None,
-                 memout_coef: Optional[torch.Tensor] = None, share: Optional["FusedLayer"] = None):
+                 memout_coef: Optional[torch.Tensor] = None, share: Optional["FusedLayer"] = None,
+                 concurrent: int = 1):
         L = lib()
         w = conv.weight.detach()
         _require_cuda(w, "layer weights")
@@ -103,6 +104,7 @@ class FusedLayer:
         else:
             d.tau, d.v_threshold, d.v_reset, d.hard_reset = 2.0, 1.0, 0.0, 1
         d.nsplit = nsplit
+        d.concurrent = int(concurrent)
         self.desc = d
         self.device = w.device
         self.T, self.B, self.C_in, self.C_out = T, B, C_in, C_out
@@ -116,8 +118,10 @@ class FusedLayer:
         self._coef = None
         ws = L.sd_conv_workspace_bytes(ctypes.byref(d)) if impl == "tc" else 0
         self._ws = torch.empty(ws, dtype=torch.uint8, device=self.device) if ws else None
-        if share is not None and share.impl == impl and share.desc.nsplit == nsplit and share.T == T:
-            # packed weights do not depend on the batch size: sub-batch plans reuse them
+        self.layout = L.sd_conv_weight_layout_tc(ctypes.byref(d)) if impl == "tc" else 0
+        if (share is not None and share.impl == impl and share.desc.nsplit == nsplit and share.T == T
+                and share.layout == self.layout):
+            # sub-batch plans reuse the packed weights when their tile configuration (the layout key) is the same
             self.wpack, self.scale, self.shift, self._coef = share.wpack, share.scale, share.shift, share._coef
             return
         scale, shift = fold_bn(conv.bias, C_out, bn, self.device)
@@ -185,14 +189,15 @@ class DenoiserPlan:
     fused tcgen05 conv+BN+LIF, conv6 on the T-summed spikes of cat(x5, x1) (linear read-out, mean over T)."""
 
     def __init__(self, model, T: int, b: int, h: int, w: int, nsplit: int = 2, impl: str = "auto",
-                 weights_from: Optional["DenoiserPlan"] = None):
+                 weights_from: Optional["DenoiserPlan"] = None, concurrent: int = 1):
         dev = model.conv1[0].weight.device
         _require_cuda(model.conv1[0].weight, "DummyModel parameters")
         self.T, self.b, self.h, self.w, self.K = T, b, h, w, model.num_embeddings
         self.device = dev
         wf = weights_from
         mk = lambda seq, sh, **kw: FusedLayer(seq[0], seq[1] if len(seq) > 1 else None, seq[2] if len(seq) > 2 else None,
-                                              T=T, B=b, H_in=h, W_in=w, nsplit=nsplit, share=sh, **kw)
+                                              T=T, B=b, H_in=h, W_in=w, nsplit=nsplit, share=sh,
+                                              concurrent=concurrent, **kw)
         self.l1 = mk(model.conv1, wf and wf.l1, in_kind=_lib.IN_REAL_CONST, out_kind=_lib.OUT_LIF, impl="simt")
         self.l2 = mk(model.conv2, wf and wf.l2, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
         self.l3 = mk(model.conv3, wf and wf.l3, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
@@ -240,18 +245,31 @@ class SamplerPlan:
 
     Sub-batches and streams: images are independent, so the shard is cut into ``n_streams`` sub-batches whose whole
     reverse-diffusion loops run on separate CUDA streams.  Each fused layer is a persistent kernel with one CTA per
-    SM; with a single stream the last, partially filled wave of every layer idles SMs (112 M-tiles x 4 N-tiles on
-    148 SMs = 3.03 waves).  With two streams the tail of one sub-batch's layer overlaps the head of the other's.
+    SM; with a single stream the last, partially filled wave of every layer idles SMs (cfg2: 49 tile pairs x 2 N
+    tiles on 74 clusters = 1.32 waves).  With several streams the tail of one sub-batch's layer overlaps the other
+    sub-batches' layers, and the small kernels (input, conv1, sampling step) hide behind the large ones.
     """
 
     def __init__(self, model, T: int, b: int, h: int, w: int, mask_id: int, n_global: Optional[int] = None,
                  shard_base: int = 0, n_streams: Optional[int] = None, nsplit: int = 2):
         import os
+        # Sub-batch plan (measured on B200, profiles/r01_experiments.md).  The tcgen05 layers work on pairs of
+        # 128-row tiles (256 rows of the dense b*h*w pixel grid), one pair per 2-SM cluster, 74 clusters:
+        #  * a shard of at most one wave of pairs runs best as up to 5 concurrent sub-batches of >= 5 pairs (their
+        #    layers pack the SMs like small items pack a bin); larger shards as 2 (fewer, longer launches; the GPU is
+        #    power-capped there);
+        #  * sub-batch sizes are cut so that their row count ends just below a multiple of 256: no half-empty pair.
+        rows_per_image = h * w
+        total_pairs = -(-b * rows_per_image // 256)
         if n_streams is None:
-            n_streams = int(os.environ.get("SD_SAMPLER_STREAMS", "2"))
+            env = os.environ.get("SD_SAMPLER_STREAMS")
+            n_streams = int(env) if env else (min(5, max(1, total_pairs // 5)) if total_pairs <= 74 else 2)
         if b < 64:
-            n_streams = 1          # small batches do not fill the SMs even once: sub-batches would only add launches
+            n_streams = 1          # sub-batches would only add launches
         n_streams = max(1, min(n_streams, b))
+        pairs_per_sub = -(-total_pairs // n_streams)
+        per = max(1, (pairs_per_sub * 256) // rows_per_image) if n_streams > 1 else b
+        n_streams = (b + per - 1) // per
         self.mask_id = int(mask_id)
         self.b, self.h, self.w, self.K = b, h, w, model.num_embeddings
         hw = h * w
@@ -262,12 +280,12 @@ class SamplerPlan:
         self.x_t = torch.empty(self.n_tokens, dtype=torch.int64, device=dev)
         self.unmasked = torch.empty(self.n_tokens, dtype=torch.uint8, device=dev)
         self.subs = []
-        per = (b + n_streams - 1) // n_streams
         lo = 0
         while lo < b:
             bi = min(per, b - lo)
             # each sub-batch has its own activation buffers (they run concurrently) but shares the packed weights
-            dp = DenoiserPlan(model, T, bi, h, w, nsplit=nsplit, weights_from=self.subs[0][0] if self.subs else None)
+            dp = DenoiserPlan(model, T, bi, h, w, nsplit=nsplit, weights_from=self.subs[0][0] if self.subs else None,
+                              concurrent=n_streams)
             self.subs.append((dp, lo, bi))
             lo += bi
         self.dp = self.subs[0][0]

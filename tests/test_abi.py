@@ -34,8 +34,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    # 17 ints + 3 floats + 2 ints, no padding; 10 pointers
-    assert ctypes.sizeof(_lib.ConvDesc) == 22 * 4
+    # 17 ints + 3 floats + 3 ints, no padding; 10 pointers
+    assert ctypes.sizeof(_lib.ConvDesc) == 23 * 4
     assert ctypes.sizeof(_lib.ConvArgs) == 10 * ctypes.sizeof(ctypes.c_void_p)
 
 

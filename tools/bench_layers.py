@@ -13,7 +13,8 @@ from spiking_diffusion_b200 import engine  # noqa: E402
 
 CONFIGS = [
     {},
-    {"SD_TC_PAIR": "1"},
+    {"SD_TC_TACC": "2"},
+    {"SD_TC_TACC": "2", "SD_TC_KBLK": "32"},
 ]
 
 

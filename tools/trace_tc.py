@@ -1,0 +1,77 @@
+"""Cycle-stamp trace of the tcgen05 conv kernel's MMA and epilogue warps per layer (GPU box).
+Usage: python tools/trace_tc.py [workload] [sub_batch]   -> where a tile's time goes: operand stalls, MMA, epilogue, hand-off."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from spiking_diffusion_b200 import _lib, engine  # noqa: E402
+
+
+def main():
+    wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg2"]
+    b = int(sys.argv[2]) if len(sys.argv) > 2 else wl["b"]
+    dev = torch.device("cuda", 0)
+    vae, den, ab, _, _ = bench.build_models(wl, dev)
+    T, hw = wl["T"], wl["hw"]
+    dp = engine.DenoiserPlan(den, T, b, hw, hw, nsplit=2)
+    x_t = torch.full((b * hw * hw,), wl["K"], dtype=torch.int64, device=dev)
+    x_t[::3] = 5
+    for _ in range(3):
+        dp.run_tokens(x_t, 7)
+    torch.cuda.synchronize()
+    lib = _lib.lib()
+    trace = torch.zeros(296 * 64, dtype=torch.int64, device=dev)
+    layers = [("conv2", dp.l2, dp.x1, dp.x2, None, None), ("conv3", dp.l3, dp.x2, dp.x3, None, None),
+              ("conv4", dp.l4, dp.x3, dp.x4, None, None), ("conv5", dp.l5, dp.x4, dp.x5, dp.x5s, None),
+              ("conv6", dp.l6, dp.x5s, dp.logits, None, dp.x1s)]
+    for n, l, xi, xo, xs, x2 in layers:
+        trace.zero_()
+        _lib.check(lib.sd_debug_tc_trace(trace.data_ptr()))
+        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); l.run(xi, xo, x2=x2, out_sum=xs); c.record()
+        torch.cuda.synchronize()
+        _lib.check(lib.sd_debug_tc_trace(None))
+        tr = trace.cpu().numpy().reshape(296, 64)
+        used = tr[:, 0] != 0
+        g = int(used.sum())
+        tr = tr[used]
+        print(f"== {n}: {a.elapsed_time(c) * 1e3:.1f} us (traced), grid {g}")
+        life = tr[:, 2] - tr[:, 0]
+        print(f"   CTA lifetime cycles: min {life.min()} median {int(np.median(life))} max {life.max()};  set-up {int(np.median(tr[:, 1] - tr[:, 0]))}")
+        # leaders own the MMA stamps (all CTAs when not paired); every CTA has epilogue stamps
+        for it in range(7):
+            base = 3 + 8 * it
+            m = tr[:, base + 0] != 0
+            e = tr[:, base + 4] != 0
+            if not e.any():
+                break
+            msg = f"   pass {it}: "
+            if m.any():
+                t = tr[m]
+                msg += (f"mma CTAs {int(m.sum())}: acc->first operands {int(np.median(t[:, base + 1] - t[:, base + 0]))}, "
+                        f"issue span {int(np.median(t[:, base + 2] - t[:, base + 0]))}, operand stall {int(np.median(t[:, base + 3]))} "
+                        f"(max {int(t[:, base + 3].max())}); ")
+                both = m & e
+                t = tr[both]
+                msg += f"acc ready after {int(np.median(t[:, base + 4] - t[:, base + 0]))} (max {int((t[:, base + 4] - t[:, base + 0]).max())}); "
+                if it > 0:
+                    pb = base - 8
+                    msg += f"hand-off epi release -> mma start {int(np.median(t[:, base + 0] - t[:, pb + 5]))}; "
+            t = tr[e]
+            msg += f"epilogue {int(np.median(t[:, base + 5] - t[:, base + 4]))} (max {int((t[:, base + 5] - t[:, base + 4]).max())}) on {int(e.sum())} CTAs"
+            print(msg)
+        # tail: last epilogue release -> exit
+        last = np.zeros(len(tr), dtype=np.int64)
+        for it in range(7):
+            v = tr[:, 3 + 8 * it + 5]
+            last = np.where(v != 0, v, last)
+        print(f"   exit - last epilogue release: median {int(np.median(tr[:, 2] - last))} max {int((tr[:, 2] - last).max())}")
+
+
+if __name__ == "__main__":
+    main()
