@@ -79,14 +79,41 @@ def summarize_launches(csvf, out, title):
     print("wrote", out)
 
 
+def write_traffic(rep, n_subs=5, workload="cfg2"):
+    """profiles/traffic.json: DRAM bytes per LAUNCH GROUP (the layer's launches of all sub-batches of one diffusion
+    step).  The capture holds 5 tcgen05 layers x n_subs sub-batches in launch order (sub-batch major)."""
+    import json
+    hdr, units, rows = raw(rep)
+    if len(rows) < 5 * n_subs:
+        print("traffic: capture too short", len(rows))
+        return
+
+    def val(r, k):
+        i = hdr.index(k)
+        v = float(r[i].replace(",", ""))
+        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(units[i].lower(), 1)
+
+    out = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per LAUNCH GROUP (the layer's launches of all "
+                       f"{n_subs} sub-batches of one diffusion step), summed from profiles/r01_conv3x3_tc.txt "
+                       "(ncu --set full, cold cache, serialised)"}
+    for li, name in enumerate(("conv2", "conv3", "conv4", "conv5", "conv6")):
+        tot = sum(val(rows[s * 5 + li], "dram__bytes_read.sum") + val(rows[s * 5 + li], "dram__bytes_write.sum")
+                  for s in range(n_subs))
+        out[f"{workload}:den.{name}:streams{n_subs}"] = int(tot)
+    json.dump(out, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
+    print("wrote traffic.json", out)
+
+
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(PROF, exist_ok=True)
     if os.path.exists(os.path.join(OUT, "p_launches.csv")):
         summarize_launches(os.path.join(OUT, "p_launches.csv"), os.path.join(PROF, f"{tag}_launch_list.txt"),
-                           "bench.py --steps 1 --warmup 1 (cfg2: b=256, T=4, K=128, 49 steps + decode), 2 sampler streams (2 x 128 images), SD_SAMPLER_GRAPH=0")
-    for rep, name, title in (("p_conv_tc.ncu-rep", "conv3x3_tc", "fused conv+BN+LIF tcgen05 kernel: den.conv2..conv6 of one diffusion step of one 128-image sub-batch (cfg2, 2 sampler streams)"),
+                           "bench.py --steps 1 --warmup 1 (cfg2: b=256, T=4, K=128, 49 steps + decode), 5 sub-batches (4 x 52 + 48 images), SD_SAMPLER_GRAPH=0")
+    for rep, name, title in (("p_conv_tc.ncu-rep", "conv3x3_tc", "fused conv+BN+LIF tcgen05 kernel: den.conv2..conv6 of one diffusion step, sub-batch by sub-batch (cfg2: 4 x 52 + 48 images)"),
                              ("p_sample.ncu-rep", "sample_step", "fused sampling-step kernel (cfg2: 12544 tokens, K=128)"),
                              ("p_conv1.ncu-rep", "conv_real_const_lif", "den.conv1: real-input conv + BN + LIF (cfg2)")):
         if os.path.exists(os.path.join(OUT, rep)):
+            if name == "conv3x3_tc":
+                write_traffic(os.path.join(OUT, rep))
             summarize_rep(os.path.join(OUT, rep), os.path.join(PROF, f"{tag}_{name}.txt"), title)
