@@ -236,6 +236,36 @@ class DenoiserPlan:
         return self.run_from_input()
 
 
+def plan_sub_batches(b: int, rows_per_image: int, n_streams: Optional[int] = None) -> list:
+    """Sizes of the concurrent sub-batches of a shard of ``b`` images (measured on B200, profiles/r01_experiments.md).
+
+    The tcgen05 layers work on pairs of 128-row tiles (256 rows of the dense b*h*w pixel grid), one pair per 2-SM
+    cluster, 74 clusters:
+     * a shard of at most one wave of pairs runs best as up to 5 concurrent sub-batches of >= 5 pairs (their layers
+       pack the SMs like small items pack a bin); larger shards as 2 (fewer, longer launches; the GPU is power-capped
+       there); below 64 images sub-batches would only add launches;
+     * sub-batch sizes are cut so that their row count ends just below a multiple of 256: no half-empty pair.
+    ``n_streams`` (or env SD_SAMPLER_STREAMS) overrides the count; the alignment rule still applies."""
+    import os
+    total_pairs = -(-b * rows_per_image // 256)
+    if n_streams is None:
+        env = os.environ.get("SD_SAMPLER_STREAMS")
+        n_streams = int(env) if env else (min(5, max(1, total_pairs // 5)) if total_pairs <= 74 else 2)
+    if b < 64:
+        n_streams = 1
+    n_streams = max(1, min(n_streams, b))
+    if n_streams == 1:
+        return [b]
+    pairs_per_sub = -(-total_pairs // n_streams)
+    per = max(1, (pairs_per_sub * 256) // rows_per_image)
+    sizes = []
+    lo = 0
+    while lo < b:
+        sizes.append(min(per, b - lo))
+        lo += sizes[-1]
+    return sizes
+
+
 class SamplerPlan:
     """AbsorbingDiffusion.sample for a fixed batch shard.
 
@@ -252,24 +282,8 @@ class SamplerPlan:
 
     def __init__(self, model, T: int, b: int, h: int, w: int, mask_id: int, n_global: Optional[int] = None,
                  shard_base: int = 0, n_streams: Optional[int] = None, nsplit: int = 2):
-        import os
-        # Sub-batch plan (measured on B200, profiles/r01_experiments.md).  The tcgen05 layers work on pairs of
-        # 128-row tiles (256 rows of the dense b*h*w pixel grid), one pair per 2-SM cluster, 74 clusters:
-        #  * a shard of at most one wave of pairs runs best as up to 5 concurrent sub-batches of >= 5 pairs (their
-        #    layers pack the SMs like small items pack a bin); larger shards as 2 (fewer, longer launches; the GPU is
-        #    power-capped there);
-        #  * sub-batch sizes are cut so that their row count ends just below a multiple of 256: no half-empty pair.
-        rows_per_image = h * w
-        total_pairs = -(-b * rows_per_image // 256)
-        if n_streams is None:
-            env = os.environ.get("SD_SAMPLER_STREAMS")
-            n_streams = int(env) if env else (min(5, max(1, total_pairs // 5)) if total_pairs <= 74 else 2)
-        if b < 64:
-            n_streams = 1          # sub-batches would only add launches
-        n_streams = max(1, min(n_streams, b))
-        pairs_per_sub = -(-total_pairs // n_streams)
-        per = max(1, (pairs_per_sub * 256) // rows_per_image) if n_streams > 1 else b
-        n_streams = (b + per - 1) // per
+        sizes = plan_sub_batches(b, h * w, n_streams)
+        n_streams = len(sizes)
         self.mask_id = int(mask_id)
         self.b, self.h, self.w, self.K = b, h, w, model.num_embeddings
         hw = h * w
@@ -281,8 +295,7 @@ class SamplerPlan:
         self.unmasked = torch.empty(self.n_tokens, dtype=torch.uint8, device=dev)
         self.subs = []
         lo = 0
-        while lo < b:
-            bi = min(per, b - lo)
+        for bi in sizes:
             # each sub-batch has its own activation buffers (they run concurrently) but shares the packed weights
             dp = DenoiserPlan(model, T, bi, h, w, nsplit=nsplit, weights_from=self.subs[0][0] if self.subs else None,
                               concurrent=n_streams)

@@ -120,3 +120,46 @@ def test_absorbing_diffusion_attributes():
     x0 = torch.randint(0, 128, (4, 1, 7, 7))
     x_t, ign, mask = ab.q_sample(x0, torch.tensor([49, 1, 25, 49]))
     assert bool((x_t[mask] == 128).all()) and bool((ign[~mask] == -1).all())
+
+
+def test_sub_batch_plan_is_pair_aligned_and_covers_the_shard(monkeypatch):
+    monkeypatch.delenv("SD_SAMPLER_STREAMS", raising=False)
+    # cfg2: 256 images x 49 rows = 49 tile pairs -> 5 sub-batches ending just below 10 pairs (2560 rows)
+    assert engine.plan_sub_batches(256, 49) == [52, 52, 52, 52, 48]
+    assert engine.plan_sub_batches(512, 49) == [256, 256]          # more than one wave of pairs: two halves
+    assert engine.plan_sub_batches(1024, 64) == [512, 512]
+    assert engine.plan_sub_batches(32, 49) == [32]                 # small batch: one launch sequence
+    assert engine.plan_sub_batches(64, 49) == [36, 28]
+    for b, rows in [(1, 49), (63, 49), (64, 49), (100, 49), (129, 49), (200, 64), (255, 49), (384, 49), (4096, 49)]:
+        for n in (None, 1, 2, 3, 5, 8):
+            sizes = engine.plan_sub_batches(b, rows, n)
+            assert sum(sizes) == b and all(s > 0 for s in sizes)
+            if len(sizes) > 1:
+                # every sub-batch but the last wastes less than one image worth of rows in its last tile pair
+                for s in sizes[:-1]:
+                    assert (-(s * rows) % 256) < rows
+    monkeypatch.setenv("SD_SAMPLER_STREAMS", "2")
+    assert engine.plan_sub_batches(256, 49) == [130, 126]
+
+
+def test_tc_weight_layout_key_depends_on_tiles_not_on_concurrent_sub_batches():
+    import ctypes
+    from spiking_diffusion_b200 import _lib
+    L = _lib.lib()
+
+    def key(B, concurrent, C_in=512, C_out=256):
+        d = _lib.ConvDesc()
+        d.T, d.B, d.C_in, d.H_in, d.W_in, d.C_out, d.H_out, d.W_out = 4, B, C_in, 7, 7, C_out, 7, 7
+        d.kh = d.kw = 3
+        d.stride = d.pad = 1
+        d.in_kind, d.out_kind, d.in_T, d.C_in0 = _lib.IN_STF, _lib.OUT_LIF, 4, C_in
+        d.tau, d.v_threshold, d.v_reset, d.hard_reset, d.nsplit, d.concurrent = 2.0, 1.0, 0.0, 1, 2, concurrent
+        return L.sd_conv_weight_layout_tc(ctypes.byref(d))
+
+    full = key(256, 1)
+    assert full > 0 and full & 1 == 1                      # N = 128, CTA pairs
+    assert key(52, 5) == full                              # a concurrent sub-batch keeps the full-size tiles
+    assert key(52, 1) != full                              # alone, the small batch is cut into narrower N tiles
+    assert key(1024, 1) == full
+    bad = _lib.ConvDesc()
+    assert L.sd_conv_weight_layout_tc(ctypes.byref(bad)) == -1
