@@ -62,6 +62,10 @@ int64_t sd_stf_bytes(int T, int B, int C, int H, int W); /* bytes of one STF ten
 /* fp32 [T,B,C,H,W] (reference layout, SJ/activation_based/layer.py:164-173) <-> STF */
 int sd_stf_from_nchw(const float* x, void* stf, int T, int B, int C, int H, int W, void* stream);
 int sd_stf_to_nchw(const void* stf, float* x, int T, int B, int C, int H, int W, void* stream);
+/* Zero-insertion 2x upsampling of an STF tensor: out (T, B, C, 2H, 2W) with out[.., 2y, 2x] = in[.., y, x] and zeros
+ * elsewhere.  ConvTranspose2d(k=3, s=2, p=1, output_padding=1) (R/snn_model/vae_model.py:139-146) equals a stride-1
+ * 3x3 convolution with flipped taps of this tensor, which is how the decoder runs on sd_conv_lif_tc. */
+int sd_stf_upsample2x(const void* in, void* out, int T, int B, int C, int H, int W, void* stream);
 
 /* Un-fused eval-mode BatchNorm2d (SJ/activation_based/layer.py:458-465 -> F.batch_norm with running stats):
  * out[n, c, i] = x[n, c, i] * scale[c] + shift[c], x fp32 [n_outer, C, HW]. */

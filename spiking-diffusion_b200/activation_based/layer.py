@@ -8,6 +8,7 @@ and runs each as ONE fused kernel, with spike tensors staying in the packed STF 
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -240,8 +241,20 @@ class SpikingSequential(nn.Sequential):
                 out_kind = _lib.OUT_REAL_SEQ
             if bn is not None and (bn.training or not bn.track_running_stats):
                 raise NotImplementedError("train-mode BatchNorm (batch statistics) is not implemented in this round")
-            fl = engine.FusedLayer(conv, bn, lif, T=T, B=B, H_in=h, W_in=w, in_kind=in_kind, out_kind=out_kind,
-                                   impl="simt" if k == 0 else "auto")
+            fl = None
+            if (k > 0 and out_kind == _lib.OUT_LIF and engine._UpsampledConvT.eligible(conv) and 2 * w + 2 <= 64
+                    and os.environ.get("SD_DECODER_TC", "1") != "0"):
+                # stride-2 transposed conv on spikes: the tcgen05 kernel on the zero-inserted upsampled input
+                cand = engine.FusedLayer(engine._UpsampledConvT(conv), bn, lif, T=T, B=B, H_in=2 * h, W_in=2 * w,
+                                         in_kind=in_kind, out_kind=out_kind, impl="auto")
+                if cand.impl == "tc":
+                    fl = cand
+                    fl.upsample_src = (conv.in_channels, h, w)
+                    fl.upsample_buf = engine.stf_empty(T, B, conv.in_channels, 2 * h, 2 * w, device)
+            if fl is None:
+                fl = engine.FusedLayer(conv, bn, lif, T=T, B=B, H_in=h, W_in=w, in_kind=in_kind, out_kind=out_kind,
+                                       impl="simt" if k == 0 else "auto")
+                fl.upsample_src = None
             plans.append(fl)
             h, w = fl.H_out, fl.W_out
         return stages, plans
@@ -273,6 +286,11 @@ class SpikingSequential(nn.Sequential):
                     check(lib().sd_state_convert(ptr(lif.v.contiguous().float()), ptr(v_planar), d.B, d.C_out, d.H_out,
                                                  d.W_out, 1, stream_ptr()))
             out = buf if plan.desc.out_kind == _lib.OUT_LIF else plan.alloc_out()
+            if plan.upsample_src is not None:
+                c_in, h_in, w_in = plan.upsample_src
+                check(lib().sd_stf_upsample2x(ptr(cur), ptr(plan.upsample_buf), plan.T, plan.B, c_in, h_in, w_in,
+                                              stream_ptr()))
+                cur = plan.upsample_buf
             plan.run(cur, out, v=v_planar)
             if lif is not None:
                 d = plan.desc

@@ -258,6 +258,25 @@ __global__ void stf_to_nchw_kernel(const __half* __restrict__ stf, float* __rest
   }
 }
 
+// Zero-insertion 2x upsampling of a spike tensor: out[t, c, b, 2y, 2x] = in[t, c, b, y, x], every other pixel 0.
+// A stride-2 ConvTranspose2d(k=3, p=1, output_padding=1) is exactly a stride-1 3x3 convolution (pad 1, flipped taps)
+// of this tensor, which puts the decoder on the tcgen05 kernel.  One thread = one 16-byte (8-channel) element.
+__global__ void __launch_bounds__(256) stf_upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
+                                                             int TC8, int B, int H, int W) {
+  const StfGeom gi(B, H, W), go(B, 2 * H, 2 * W);
+  const int64_t rows_out = (int64_t)B * go.P;
+  const int64_t total = (int64_t)TC8 * rows_out;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t plane = i / rows_out, r = i - plane * rows_out;
+    const int b = (int)(r / go.P);
+    const int pp = (int)(r - (int64_t)b * go.P);
+    const int oy = pp / go.W, ox = pp - oy * go.W;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (((oy | ox) & 1) == 0) v = in[plane * gi.R_alloc + gi.row(b, oy >> 1, ox >> 1)];
+    out[plane * go.R_alloc + go.G + r] = v;
+  }
+}
+
 // y[n, c, i] = x[n, c, i] * scale[c] + shift[c]   (un-fused eval-mode BatchNorm2d, SJ/activation_based/layer.py:458-465)
 __global__ void channel_affine_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                       const float* __restrict__ shift, float* __restrict__ out, int64_t total, int C,
@@ -404,6 +423,18 @@ int sd_stf_from_nchw(const float* x, void* stf, int T, int B, int C, int H, int 
   SD_CUDA(cudaMemsetAsync(stf, 0, (size_t)sd_stf_bytes(T, B, C, H, W), st));
   int64_t n = (int64_t)T * B * C * H * W;
   stf_from_nchw_kernel<<<grid_for(n), 256, 0, st>>>(x, (__half*)stf, T, B, C, H, W);
+  SD_LAUNCH_CHECK();
+  return SD_OK;
+}
+
+int sd_stf_upsample2x(const void* in, void* out, int T, int B, int C, int H, int W, void* stream) {
+  SD_REQUIRE(T >= 1 && B >= 1 && C >= 1 && H >= 1 && W >= 1, "stf_upsample2x: bad shape");
+  SD_REQUIRE(in && out && in != out, "stf_upsample2x: null or aliased pointer argument");
+  SD_REQUIRE((((uintptr_t)in | (uintptr_t)out) & 15) == 0, "stf_upsample2x: buffers must be 16-byte aligned");
+  SD_DEVICE_OR_RETURN();
+  const int TC8 = T * c8(C);
+  const int64_t n = (int64_t)TC8 * B * 4 * H * W;
+  stf_upsample2x_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>((const uint4*)in, (uint4*)out, TC8, B, H, W);
   SD_LAUNCH_CHECK();
   return SD_OK;
 }

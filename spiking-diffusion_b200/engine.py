@@ -106,6 +106,7 @@ class FusedLayer:
         d.nsplit = nsplit
         d.concurrent = int(concurrent)
         self.desc = d
+        self.algorithmic_flops = None   # set when the layer runs a mathematically equal but larger problem
         self.device = w.device
         self.T, self.B, self.C_in, self.C_out = T, B, C_in, C_out
         self.H_in, self.W_in, self.H_out, self.W_out = H_in, W_in, H_out, W_out
@@ -144,6 +145,8 @@ class FusedLayer:
 
     def flops(self) -> int:
         """Dense algorithmic FLOPs (2*MAC) of one call, counted as SURVEY.md section 8(d) does."""
+        if self.algorithmic_flops is not None:
+            return self.algorithmic_flops
         d = self.desc
         if d.transposed:
             mac = d.C_in * d.C_out * d.kh * d.kw * d.H_in * d.W_in
@@ -401,6 +404,27 @@ class SamplerPlan:
 
 
 # --------------------------------------------------------------------------------------------------
+class _UpsampledConvT:
+    """ConvTranspose2d(k=3, s=2, p=1, output_padding=1) restated as the stride-1 3x3 convolution (pad 1) it equals on the
+    zero-inserted 2x upsampled input: out[o] = sum_i in[i] w[o + 1 - 2i]  ==  sum_k' u[o - 1 + k'] w[2 - k'] with
+    u[2i] = in[i].  Carries the attributes FusedLayer reads from a conv module."""
+
+    def __init__(self, convt):
+        # [C_in, C_out, 3, 3] -> [C_out, C_in, 3, 3], taps flipped
+        self.weight = convt.weight.detach().transpose(0, 1).flip(2, 3).contiguous()
+        self.bias = convt.bias
+        self.kernel_size, self.stride, self.padding, self.dilation, self.groups = (3, 3), (1, 1), (1, 1), (1, 1), 1
+        self.transposed = False
+        self.in_channels, self.out_channels = convt.in_channels, convt.out_channels
+
+    @staticmethod
+    def eligible(convt) -> bool:
+        return (bool(getattr(convt, "transposed", isinstance(convt, torch.nn.ConvTranspose2d)))
+                and tuple(convt.kernel_size) == (3, 3) and tuple(convt.stride) == (2, 2)
+                and tuple(convt.padding) == (1, 1) and tuple(convt.output_padding) == (1, 1)
+                and convt.in_channels % 16 == 0 and convt.out_channels % 16 == 0)
+
+
 class VQVAEPlan:
     """Encoder -> quantiser -> spike generator -> decoder of SNN_VQVAE for a fixed (T, B, H, W)."""
 
@@ -419,8 +443,27 @@ class VQVAEPlan:
         self.h, self.w = self.e3.H_out, self.e3.W_out
         self.gen = mk(vq.poisson[0], vq.poisson[1], vq.poisson[2], self.h, self.w, in_kind=_lib.IN_REAL_CONST,
                       out_kind=_lib.OUT_LIF, impl="simt")
-        self.d1 = mk(dec[0], dec[1], dec[2], self.h, self.w, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF)
-        self.d2 = mk(dec[3], dec[4], dec[5], self.d1.H_out, self.d1.W_out, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF)
+        # Decoder: the two stride-2 transposed convolutions run on the tcgen05 kernel as stride-1 convolutions of the
+        # zero-inserted upsampled spikes (4x the MMAs of the algorithm, still several times faster than CUDA cores);
+        # SD_DECODER_TC=0 keeps the CUDA-core kernels (used by the tests to cross-check the two paths).
+        import os
+        self.tc_decoder = (os.environ.get("SD_DECODER_TC", "1") != "0" and _UpsampledConvT.eligible(dec[0])
+                           and _UpsampledConvT.eligible(dec[3]) and 4 * self.w + 2 <= 64)
+        if self.tc_decoder:
+            self.d1 = mk(_UpsampledConvT(dec[0]), dec[1], dec[2], 2 * self.h, 2 * self.w, in_kind=_lib.IN_STF,
+                         out_kind=_lib.OUT_LIF)
+            self.d2 = mk(_UpsampledConvT(dec[3]), dec[4], dec[5], 4 * self.h, 4 * self.w, in_kind=_lib.IN_STF,
+                         out_kind=_lib.OUT_LIF)
+            self.tc_decoder = self.d1.impl == "tc" and self.d2.impl == "tc"
+        if self.tc_decoder:
+            self.d1.algorithmic_flops = self.d1.flops() // 4
+            self.d2.algorithmic_flops = self.d2.flops() // 4
+            self.up0 = stf_empty(T, B, dec[0].in_channels, 2 * self.h, 2 * self.w, dev)
+            self.up1 = stf_empty(T, B, dec[3].in_channels, 4 * self.h, 4 * self.w, dev)
+        else:
+            self.d1 = mk(dec[0], dec[1], dec[2], self.h, self.w, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF)
+            self.d2 = mk(dec[3], dec[4], dec[5], self.d1.H_out, self.d1.W_out, in_kind=_lib.IN_STF,
+                         out_kind=_lib.OUT_LIF)
         self.d3 = mk(dec[6], None, None, self.d2.H_out, self.d2.W_out, in_kind=_lib.IN_STF,
                      out_kind=_lib.OUT_MEMOUT_TANH, memout_coef=model.memout.coef)
         self.s1, self.s2, self.s3 = self.e1.alloc_out(), self.e2.alloc_out(), self.e3.alloc_out()
@@ -460,8 +503,16 @@ class VQVAEPlan:
         return self.sg
 
     def decode(self, e_stf: torch.Tensor) -> torch.Tensor:
-        self.d1.run(e_stf, self.sd1)
-        self.d2.run(self.sd1, self.sd2)
+        if self.tc_decoder:
+            L, d1, d2 = lib(), self.d1.desc, self.d2.desc
+            check(L.sd_stf_upsample2x(ptr(e_stf), ptr(self.up0), self.T, self.B, d1.C_in, self.h, self.w, stream_ptr()))
+            self.d1.run(self.up0, self.sd1)
+            check(L.sd_stf_upsample2x(ptr(self.sd1), ptr(self.up1), self.T, self.B, d2.C_in, 2 * self.h, 2 * self.w,
+                                      stream_ptr()))
+            self.d2.run(self.up1, self.sd2)
+        else:
+            self.d1.run(e_stf, self.sd1)
+            self.d2.run(self.sd1, self.sd2)
         self.d3.run(self.sd2, self.recon)
         return self.recon
 

@@ -209,3 +209,43 @@ def test_tc_rejects_unsupported_shapes():
     seq, _ = make_block(32, 64, 3, 2, 1, seed=1)
     with pytest.raises(ValueError):
         tc_layer(seq, 4, 2, 14, _lib.OUT_LIF, 2)      # stride 2
+
+
+# ---- stride-2 transposed convolution on the tcgen05 kernel (decoder) -----------------------------------------
+@pytest.mark.parametrize("T,B,C,H,W", [(4, 3, 16, 7, 7), (1, 2, 8, 5, 3), (16, 1, 24, 14, 14)])
+def test_stf_upsample2x_is_zero_insertion(T, B, C, H, W):
+    s = spikes((T, B, C, H, W), 0.3, 11).cuda()
+    out = engine.stf_empty(T, B, C, 2 * H, 2 * W, s.device)
+    out.fill_(7.0)   # every valid row must be overwritten
+    _lib.check(_lib.lib().sd_stf_upsample2x(_lib.ptr(engine.stf_from_nchw(s)), _lib.ptr(out), T, B, C, H, W,
+                                            _lib.stream_ptr()))
+    got = engine.stf_to_nchw(out, T, B, C, 2 * H, 2 * W)
+    ref = torch.zeros_like(got)
+    ref[..., ::2, ::2] = s
+    assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("cin,cout,B,H,T", [(16, 64, 5, 7, 4), (64, 32, 3, 14, 4), (64, 32, 2, 14, 16), (16, 64, 3, 8, 8)])
+def test_transposed_conv_as_upsampled_tc_conv_matches_oracle_and_simt(cin, cout, B, H, T):
+    """ConvTranspose2d(k3, s2, p1, op1) + BN + LIF: the tcgen05 route (zero-insertion + flipped 3x3 conv) against the
+    oracle's F.conv_transpose2d and against the CUDA-core transposed kernel."""
+    seq, p = make_block(cin, cout, 3, stride=2, pad=1, transposed=True, op=1, seed=5)
+    conv, bn, lif = seq[0], seq[1], seq[2]
+    assert engine._UpsampledConvT.eligible(conv)
+    s_in = spikes((T, B, cin, H, H), 0.15, 9)
+    cur, s_ref, h_ref = oracle_layer(s_in, p, stride=2, padding=1, transposed=True, output_padding=1)
+    x_stf = engine.stf_from_nchw(s_in.cuda())
+    up = engine.stf_empty(T, B, cin, 2 * H, 2 * H, x_stf.device)
+    _lib.check(_lib.lib().sd_stf_upsample2x(_lib.ptr(x_stf), _lib.ptr(up), T, B, cin, H, H, _lib.stream_ptr()))
+    tc = engine.FusedLayer(engine._UpsampledConvT(conv), bn, lif, T=T, B=B, H_in=2 * H, W_in=2 * H,
+                           in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl="tc")
+    simt = engine.FusedLayer(conv, bn, lif, T=T, B=B, H_in=H, W_in=H, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF,
+                             impl="simt")
+    o_tc, o_simt = tc.alloc_out(), simt.alloc_out()
+    tc.run(up, o_tc)
+    simt.run(x_stf, o_simt)
+    g_tc = engine.stf_to_nchw(o_tc, T, B, cout, 2 * H, 2 * H).cpu()
+    g_simt = engine.stf_to_nchw(o_simt, T, B, cout, 2 * H, 2 * H).cpu()
+    assert_spikes_match(g_tc, s_ref, h_ref, "convT on tcgen05")
+    assert_spikes_match(g_simt, s_ref, h_ref, "convT on CUDA cores")
+    assert float((g_tc != g_simt).float().mean()) <= 1e-4
