@@ -66,6 +66,10 @@ int sd_stf_to_nchw(const void* stf, float* x, int T, int B, int C, int H, int W,
  * elsewhere.  ConvTranspose2d(k=3, s=2, p=1, output_padding=1) (R/snn_model/vae_model.py:139-146) equals a stride-1
  * 3x3 convolution with flipped taps of this tensor, which is how the decoder runs on sd_conv_lif_tc. */
 int sd_stf_upsample2x(const void* in, void* out, int T, int B, int C, int H, int W, void* stream);
+/* out (T, B, C, ceil(H/2), ceil(W/2)) with out[.., y, x] = in[.., 2y, 2x]: the outputs of Conv2d(k=3, s=2, p=1)
+ * (R/snn_model/vae_model.py:107-114) are the even positions of the stride-1 convolution computed by sd_conv_lif_tc
+ * (the LIF recurrence is per neuron, so dropping the other positions afterwards is exact). */
+int sd_stf_subsample2x(const void* in, void* out, int T, int B, int C, int H, int W, void* stream);
 
 /* Un-fused eval-mode BatchNorm2d (SJ/activation_based/layer.py:458-465 -> F.batch_norm with running stats):
  * out[n, c, i] = x[n, c, i] * scale[c] + shift[c], x fp32 [n_outer, C, HW]. */

@@ -445,6 +445,99 @@ __global__ void __launch_bounds__(128) conv_spike8_kernel(const SimtParams p) {
   }
 }
 
+
+// Spike-input layer with a handful of output channels and the memout + tanh tail (dec.convT3: 32 -> image channels,
+// R/snn_model/vae_model.py:147,185).  One thread = one output pixel x all (<= NCO) output channels x all T timesteps;
+// the whole weight tensor [tap][ci][co] sits in shared memory and is read as warp-uniform broadcasts.  The FMA order
+// per output (tap, input channel) is the one of conv_spike8_kernel, so both give the same bits.
+template <int TMAX, int NCO>
+__global__ void __launch_bounds__(128) conv_spike_fewout_memout_kernel(const SimtParams p) {
+  extern __shared__ float w_s[];   // [taps][Cin][NCO]
+  const sd_conv_desc& d = p.d;
+  const int T = d.T, Cout = d.C_out, Cin = d.C_in, taps = d.kh * d.kw;
+  for (int i = threadIdx.x; i < taps * Cin * NCO; i += blockDim.x) {
+    const int j = i % NCO, r = i / NCO;
+    w_s[i] = j < Cout ? p.w[(int64_t)r * Cout + j] : 0.f;
+  }
+  __syncthreads();
+  const StfGeom gin(d.B, d.H_in, d.W_in);
+  const int Cin8_0 = c8(d.C_in0), Cin8_1 = c8(Cin - d.C_in0);
+  const int64_t npix = (int64_t)d.B * d.H_out * d.W_out;
+  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(pix % d.W_out);
+    const int64_t r0 = pix / d.W_out;
+    const int oy = (int)(r0 % d.H_out);
+    const int b = (int)(r0 / d.H_out);
+    float acc[TMAX][NCO];
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t)
+#pragma unroll
+      for (int j = 0; j < NCO; ++j) acc[t][j] = 0.f;
+    for (int ky = 0; ky < d.kh; ++ky) {
+      int iy;
+      if (d.transposed) {
+        const int ny = oy + d.pad - ky;
+        if (ny < 0 || ny % d.stride) continue;
+        iy = ny / d.stride;
+      } else {
+        iy = oy * d.stride - d.pad + ky;
+      }
+      if (iy < 0 || iy >= d.H_in) continue;
+      for (int kx = 0; kx < d.kw; ++kx) {
+        int ix;
+        if (d.transposed) {
+          const int nx = ox + d.pad - kx;
+          if (nx < 0 || nx % d.stride) continue;
+          ix = nx / d.stride;
+        } else {
+          ix = ox * d.stride - d.pad + kx;
+        }
+        if (ix < 0 || ix >= d.W_in) continue;
+        const float* wt = w_s + (ky * d.kw + kx) * Cin * NCO;
+        const int64_t row = gin.row(b, iy, ix);
+        for (int cc = 0; cc < Cin; cc += 8) {
+          const bool seg1 = cc >= d.C_in0;
+          const __half* base = seg1 ? (const __half*)p.in2 : (const __half*)p.in;
+          const int C8s = seg1 ? Cin8_1 : Cin8_0;
+          const int cl = seg1 ? cc - d.C_in0 : cc;
+          float w[8][NCO];
+#pragma unroll
+          for (int ci = 0; ci < 8; ++ci)
+#pragma unroll
+            for (int j = 0; j < NCO; ++j) w[ci][j] = (cc + ci < Cin) ? wt[(cc + ci) * NCO + j] : 0.f;
+#pragma unroll
+          for (int t = 0; t < TMAX; ++t) {
+            if (t < T) {
+              const uint4 raw = *reinterpret_cast<const uint4*>(base + gin.at(t, C8s, cl, row));
+              const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 f = __half22float2(h2[q]);
+#pragma unroll
+                for (int j = 0; j < NCO; ++j) {
+                  acc[t][j] = fmaf(f.x, w[2 * q][j], acc[t][j]);
+                  acc[t][j] = fmaf(f.y, w[2 * q + 1][j], acc[t][j]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NCO; ++j) {
+      if (j < Cout) {
+        const float sc = p.scale[j], sh = p.shift[j];
+        float m = 0.f;
+#pragma unroll
+        for (int t = 0; t < TMAX; ++t)
+          if (t < T) m = __fadd_rn(m, __fmul_rn(fmaf(acc[t][j], sc, sh), p.coef.c[t]));
+        ((float*)p.out)[(((int64_t)b * Cout + j) * d.H_out + oy) * d.W_out + ox] = tanhf(m);
+      }
+    }
+  }
+}
+
 // w (reference layout) -> [tap][ci][co]
 __global__ void pack_simt_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int kh,
                                  int kw, int transposed) {
@@ -542,6 +635,24 @@ int sd_conv_lif_simt(const sd_conv_desc* d, const sd_conv_args* a, void* stream)
     return SD_OK;
   }
   static const bool force_generic = getenv("SD_SIMT_GENERIC") != nullptr;   // debugging aid: exact-order generic kernel
+  if (!force_generic && d->in_kind == SD_IN_STF && d->in_T == d->T && d->T <= 16 && d->out_kind == SD_OUT_MEMOUT_TANH &&
+      d->C_out <= 4 && (int64_t)d->kh * d->kw * d->C_in * 4 * sizeof(float) <= 48 * 1024) {
+    const int64_t npix = (int64_t)d->B * d->H_out * d->W_out;
+    int64_t bl = (npix + 127) / 128;
+    if (bl > cap * 2) bl = cap * 2;
+    const int nco = d->C_out <= 1 ? 1 : (d->C_out <= 2 ? 2 : 4);
+    const size_t smem = (size_t)d->kh * d->kw * d->C_in * nco * sizeof(float);
+#define SD_FEWOUT(TM)                                                                                          \
+  do {                                                                                                         \
+    if (nco == 1) conv_spike_fewout_memout_kernel<TM, 1><<<(unsigned)bl, 128, smem, st>>>(p);                  \
+    else if (nco == 2) conv_spike_fewout_memout_kernel<TM, 2><<<(unsigned)bl, 128, smem, st>>>(p);             \
+    else conv_spike_fewout_memout_kernel<TM, 4><<<(unsigned)bl, 128, smem, st>>>(p);                           \
+  } while (0)
+    if (d->T <= 4) SD_FEWOUT(4); else if (d->T <= 8) SD_FEWOUT(8); else SD_FEWOUT(16);
+#undef SD_FEWOUT
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+  }
   if (!force_generic && d->in_kind == SD_IN_STF && d->in_T == d->T && d->T <= 8 &&
       (d->out_kind == SD_OUT_MEMOUT_TANH || (d->out_kind == SD_OUT_LIF && d->C_out % 8 == 0))) {
     int64_t n8 = (int64_t)d->B * d->H_out * d->W_out * ((d->C_out + 7) / 8);

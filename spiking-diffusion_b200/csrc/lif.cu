@@ -277,6 +277,22 @@ __global__ void __launch_bounds__(256) stf_upsample2x_kernel(const uint4* __rest
   }
 }
 
+// out[t, c, b, y, x] = in[t, c, b, 2y, 2x]: the outputs of a stride-2 3x3 convolution (pad 1) are the even positions of
+// the stride-1 convolution, which runs on the tcgen05 kernel.
+__global__ void __launch_bounds__(256) stf_subsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
+                                                              int TC8, int B, int H, int W, int Ho, int Wo) {
+  const StfGeom gi(B, H, W), go(B, Ho, Wo);
+  const int64_t rows_out = (int64_t)B * go.P;
+  const int64_t total = (int64_t)TC8 * rows_out;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t plane = i / rows_out, r = i - plane * rows_out;
+    const int b = (int)(r / go.P);
+    const int pp = (int)(r - (int64_t)b * go.P);
+    const int oy = pp / go.W, ox = pp - oy * go.W;
+    out[plane * go.R_alloc + go.G + r] = in[plane * gi.R_alloc + gi.row(b, 2 * oy, 2 * ox)];
+  }
+}
+
 // y[n, c, i] = x[n, c, i] * scale[c] + shift[c]   (un-fused eval-mode BatchNorm2d, SJ/activation_based/layer.py:458-465)
 __global__ void channel_affine_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                       const float* __restrict__ shift, float* __restrict__ out, int64_t total, int C,
@@ -435,6 +451,18 @@ int sd_stf_upsample2x(const void* in, void* out, int T, int B, int C, int H, int
   const int TC8 = T * c8(C);
   const int64_t n = (int64_t)TC8 * B * 4 * H * W;
   stf_upsample2x_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>((const uint4*)in, (uint4*)out, TC8, B, H, W);
+  SD_LAUNCH_CHECK();
+  return SD_OK;
+}
+
+int sd_stf_subsample2x(const void* in, void* out, int T, int B, int C, int H, int W, void* stream) {
+  SD_REQUIRE(T >= 1 && B >= 1 && C >= 1 && H >= 1 && W >= 1, "stf_subsample2x: bad shape");
+  SD_REQUIRE(in && out && in != out, "stf_subsample2x: null or aliased pointer argument");
+  SD_REQUIRE((((uintptr_t)in | (uintptr_t)out) & 15) == 0, "stf_subsample2x: buffers must be 16-byte aligned");
+  SD_DEVICE_OR_RETURN();
+  const int TC8 = T * c8(C), Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const int64_t n = (int64_t)TC8 * B * Ho * Wo;
+  stf_subsample2x_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>((const uint4*)in, (uint4*)out, TC8, B, H, W, Ho, Wo);
   SD_LAUNCH_CHECK();
   return SD_OK;
 }

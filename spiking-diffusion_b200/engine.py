@@ -425,6 +425,23 @@ class _UpsampledConvT:
                 and convt.in_channels % 16 == 0 and convt.out_channels % 16 == 0)
 
 
+class _Stride1Conv:
+    """Conv2d(k=3, s=2, p=1) restated as the stride-1 convolution whose even output positions it is."""
+
+    def __init__(self, conv):
+        self.weight, self.bias = conv.weight, conv.bias
+        self.kernel_size, self.stride, self.padding, self.dilation, self.groups = (3, 3), (1, 1), (1, 1), (1, 1), 1
+        self.transposed = False
+        self.in_channels, self.out_channels = conv.in_channels, conv.out_channels
+
+    @staticmethod
+    def eligible(conv) -> bool:
+        return (not bool(getattr(conv, "transposed", isinstance(conv, torch.nn.ConvTranspose2d)))
+                and tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == (2, 2)
+                and tuple(conv.padding) == (1, 1) and tuple(conv.dilation) == (1, 1) and conv.groups == 1
+                and conv.in_channels % 16 == 0 and conv.out_channels % 16 == 0)
+
+
 class VQVAEPlan:
     """Encoder -> quantiser -> spike generator -> decoder of SNN_VQVAE for a fixed (T, B, H, W)."""
 
@@ -438,7 +455,21 @@ class VQVAEPlan:
         mk = lambda conv, bn, lif, Hi, Wi, **kw: FusedLayer(conv, bn, lif, T=T, B=B, H_in=Hi, W_in=Wi, nsplit=nsplit, **kw)
         self.e1 = mk(enc[0], enc[1], enc[2], H, W, in_kind=_lib.IN_REAL_SEQ, out_kind=_lib.OUT_LIF, impl="simt")
         self.e1c = mk(enc[0], enc[1], enc[2], H, W, in_kind=_lib.IN_REAL_CONST, out_kind=_lib.OUT_LIF, impl="simt")
-        self.e2 = mk(enc[3], enc[4], enc[5], self.e1.H_out, self.e1.W_out, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF)
+        # enc.conv2 (stride 2, spike input): on the tcgen05 kernel at stride 1, even positions kept afterwards
+        # (4x the MMAs of the algorithm, several times faster than CUDA cores); SD_ENCODER_TC=0 keeps the CUDA-core kernel
+        import os
+        self.tc_encoder = (os.environ.get("SD_ENCODER_TC", "1") != "0" and _Stride1Conv.eligible(enc[3])
+                           and self.e1.W_out + 2 <= 64)
+        if self.tc_encoder:
+            self.e2 = mk(_Stride1Conv(enc[3]), enc[4], enc[5], self.e1.H_out, self.e1.W_out, in_kind=_lib.IN_STF,
+                         out_kind=_lib.OUT_LIF)
+            self.tc_encoder = self.e2.impl == "tc"
+        if self.tc_encoder:
+            self.e2.algorithmic_flops = self.e2.flops() // 4
+            self.s2_full = self.e2.alloc_out()
+            self.e2.H_out, self.e2.W_out = (self.e1.H_out + 1) // 2, (self.e1.W_out + 1) // 2
+        else:
+            self.e2 = mk(enc[3], enc[4], enc[5], self.e1.H_out, self.e1.W_out, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF)
         self.e3 = mk(enc[6], enc[7], enc[8], self.e2.H_out, self.e2.W_out, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF)
         self.h, self.w = self.e3.H_out, self.e3.W_out
         self.gen = mk(vq.poisson[0], vq.poisson[1], vq.poisson[2], self.h, self.w, in_kind=_lib.IN_REAL_CONST,
@@ -466,7 +497,8 @@ class VQVAEPlan:
                          out_kind=_lib.OUT_LIF)
         self.d3 = mk(dec[6], None, None, self.d2.H_out, self.d2.W_out, in_kind=_lib.IN_STF,
                      out_kind=_lib.OUT_MEMOUT_TANH, memout_coef=model.memout.coef)
-        self.s1, self.s2, self.s3 = self.e1.alloc_out(), self.e2.alloc_out(), self.e3.alloc_out()
+        self.s1, self.s3 = self.e1.alloc_out(), self.e3.alloc_out()
+        self.s2 = stf_empty(T, B, self.e2.C_out, self.e2.H_out, self.e2.W_out, dev)
         self.z = torch.empty((B * self.h * self.w, self.D), dtype=torch.float32, device=dev)
         self.idx = torch.empty(B * self.h * self.w, dtype=torch.int64, device=dev)
         self.margin = torch.empty(B * self.h * self.w, dtype=torch.float32, device=dev)
@@ -482,7 +514,12 @@ class VQVAEPlan:
             self.e1c.run(x.contiguous(), self.s1)
         else:
             self.e1.run(x.contiguous(), self.s1)
-        self.e2.run(self.s1, self.s2)
+        if self.tc_encoder:
+            self.e2.run(self.s1, self.s2_full)
+            check(lib().sd_stf_subsample2x(ptr(self.s2_full), ptr(self.s2), self.T, self.B, self.e2.C_out,
+                                           self.e1.H_out, self.e1.W_out, stream_ptr()))
+        else:
+            self.e2.run(self.s1, self.s2)
         self.e3.run(self.s2, self.s3)
         return self.s3
 

@@ -249,3 +249,40 @@ def test_transposed_conv_as_upsampled_tc_conv_matches_oracle_and_simt(cin, cout,
     assert_spikes_match(g_tc, s_ref, h_ref, "convT on tcgen05")
     assert_spikes_match(g_simt, s_ref, h_ref, "convT on CUDA cores")
     assert float((g_tc != g_simt).float().mean()) <= 1e-4
+
+
+@pytest.mark.parametrize("T,B,C,H,W", [(4, 3, 16, 14, 14), (1, 2, 8, 7, 5), (16, 1, 24, 8, 8)])
+def test_stf_subsample2x_keeps_even_positions(T, B, C, H, W):
+    s = spikes((T, B, C, H, W), 0.3, 12).cuda()
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    out = engine.stf_empty(T, B, C, Ho, Wo, s.device)
+    _lib.check(_lib.lib().sd_stf_subsample2x(_lib.ptr(engine.stf_from_nchw(s)), _lib.ptr(out), T, B, C, H, W,
+                                             _lib.stream_ptr()))
+    assert torch.equal(engine.stf_to_nchw(out, T, B, C, Ho, Wo), s[..., ::2, ::2])
+
+
+@pytest.mark.parametrize("cin,cout,B,H,T", [(32, 64, 5, 14, 4), (32, 64, 2, 14, 16), (16, 32, 3, 7, 8)])
+def test_stride2_conv_as_subsampled_tc_conv_matches_oracle_and_simt(cin, cout, B, H, T):
+    """Conv2d(k3, s2, p1) + BN + LIF: stride-1 tcgen05 conv followed by the even-position pick, against the oracle's
+    strided F.conv2d and against the CUDA-core strided kernel."""
+    seq, p = make_block(cin, cout, 3, stride=2, pad=1, seed=6)
+    conv, bn, lif = seq[0], seq[1], seq[2]
+    assert engine._Stride1Conv.eligible(conv)
+    s_in = spikes((T, B, cin, H, H), 0.15, 10)
+    cur, s_ref, h_ref = oracle_layer(s_in, p, stride=2, padding=1)
+    Ho = (H + 1) // 2
+    x_stf = engine.stf_from_nchw(s_in.cuda())
+    tc = engine.FusedLayer(engine._Stride1Conv(conv), bn, lif, T=T, B=B, H_in=H, W_in=H, in_kind=_lib.IN_STF,
+                           out_kind=_lib.OUT_LIF, impl="tc")
+    simt = engine.FusedLayer(conv, bn, lif, T=T, B=B, H_in=H, W_in=H, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF,
+                             impl="simt")
+    full, o_simt = tc.alloc_out(), simt.alloc_out()
+    tc.run(x_stf, full)
+    o_tc = engine.stf_empty(T, B, cout, Ho, Ho, x_stf.device)
+    _lib.check(_lib.lib().sd_stf_subsample2x(_lib.ptr(full), _lib.ptr(o_tc), T, B, cout, H, H, _lib.stream_ptr()))
+    simt.run(x_stf, o_simt)
+    g_tc = engine.stf_to_nchw(o_tc, T, B, cout, Ho, Ho).cpu()
+    g_simt = engine.stf_to_nchw(o_simt, T, B, cout, Ho, Ho).cpu()
+    assert_spikes_match(g_tc, s_ref, h_ref, "strided conv on tcgen05")
+    assert_spikes_match(g_simt, s_ref, h_ref, "strided conv on CUDA cores")
+    assert float((g_tc != g_simt).float().mean()) <= 1e-4

@@ -61,6 +61,27 @@ def main():
         "gather+generator": round(gpu_time(lambda: plan.generate(idx)), 4),
         "decode": round(gpu_time(lambda: plan.decode(e)), 4),
     }
+    if plan.tc_decoder:
+        from spiking_diffusion_b200._lib import check, lib, ptr, stream_ptr
+        L, d1, d2 = lib(), plan.d1.desc, plan.d2.desc
+        res["decode_stages_ms"] = {
+            "upsample0": round(gpu_time(lambda: check(L.sd_stf_upsample2x(ptr(e), ptr(plan.up0), T, B, d1.C_in, plan.h, plan.w, stream_ptr()))), 4),
+            "convT1 (tc)": round(gpu_time(lambda: plan.d1.run(plan.up0, plan.sd1)), 4),
+            "upsample1": round(gpu_time(lambda: check(L.sd_stf_upsample2x(ptr(plan.sd1), ptr(plan.up1), T, B, d2.C_in, 2 * plan.h, 2 * plan.w, stream_ptr()))), 4),
+            "convT2 (tc)": round(gpu_time(lambda: plan.d2.run(plan.up1, plan.sd2)), 4),
+            "convT3+memout+tanh": round(gpu_time(lambda: plan.d3.run(plan.sd2, plan.recon)), 4),
+        }
+    else:
+        res["decode_stages_ms"] = {
+            "convT1": round(gpu_time(lambda: plan.d1.run(e, plan.sd1)), 4),
+            "convT2": round(gpu_time(lambda: plan.d2.run(plan.sd1, plan.sd2)), 4),
+            "convT3+memout+tanh": round(gpu_time(lambda: plan.d3.run(plan.sd2, plan.recon)), 4),
+        }
+    res["encode_stages_ms"] = {
+        "conv1 (const input)": round(gpu_time(lambda: plan.e1c.run(ig, plan.s1)), 4),
+        "conv2 s2": round(gpu_time(lambda: plan.e2.run(plan.s1, plan.s2)), 4),
+        "conv3 1x1": round(gpu_time(lambda: plan.e3.run(plan.s2, plan.s3)), 4),
+    }
     res["images_per_s_gpu"] = round(B / res["plan_forward_ms"] * 1e3, 1)
     # CPU leg: the oracle port of the reference on all host threads
     cores = os.cpu_count() or 1
