@@ -208,7 +208,7 @@ int sd_conv_tc_supported(const sd_conv_desc* d);
  * counterpart. */
 int sd_debug_tc_trace(void* buf);
 
-/* ---- (f.1) training-path kernels (first correct versions, CUDA cores) ------------------------------------------
+/* ---- (f.1) training-path kernels (fp32 on CUDA cores: tiled implicit GEMMs) -------------------------------------
  * The reference trains through torch autograd over F.conv2d / F.conv_transpose2d / F.batch_norm
  * (SJ/activation_based/layer.py:164-173,316-325,458-465).  The input gradient of a convolution is the adjoint
  * convolution and is computed with sd_conv_lif_simt (SD_IN_REAL_SEQ -> SD_OUT_REAL_SEQ); these entry points add the
@@ -217,9 +217,11 @@ int sd_debug_tc_trace(void* buf);
  *   grad_w in the reference parameter layout ([C_out,C_in,kh,kw] or [C_in,C_out,kh,kw]), grad_bias [C_out] or NULL.
  * sd_bn_train_forward: x, y fp32 [n_outer, C, HW]; batch mean / biased variance per channel are written for the
  *   backward pass and the caller's running-statistics update.
- */
+ * workspace: sd_conv_wgrad_workspace_bytes(d) bytes of scratch (partial sums of the split reduction, added in a fixed
+ *   order: the result is deterministic). */
+int64_t sd_conv_wgrad_workspace_bytes(const sd_conv_desc* d);
 int sd_conv_wgrad(const sd_conv_desc* d, const float* x, const float* grad_out, float* grad_w, float* grad_bias_or_null,
-                  void* stream);
+                  void* workspace, void* stream);
 int sd_bn_train_forward(const float* x, const float* gamma_or_null, const float* beta_or_null, float* y,
                         float* mean_out, float* var_out, int64_t n_outer, int C, int64_t HW, float eps, void* stream);
 int sd_bn_backward(const float* x, const float* grad_out, const float* mean, const float* var,

@@ -72,7 +72,8 @@ class _ConvFn(torch.autograd.Function):
             gw = torch.empty_like(weight, dtype=torch.float32)
             gb = torch.empty(d.C_out, dtype=torch.float32, device=gy.device) if has_bias else None
             import ctypes
-            check(lib().sd_conv_wgrad(ctypes.byref(d), ptr(x5), ptr(gy), ptr(gw), ptr(gb), stream_ptr()))
+            ws = torch.empty(lib().sd_conv_wgrad_workspace_bytes(ctypes.byref(d)), dtype=torch.uint8, device=gy.device)
+            check(lib().sd_conv_wgrad(ctypes.byref(d), ptr(x5), ptr(gy), ptr(gw), ptr(gb), ptr(ws), stream_ptr()))
         return gx, gw, gb, None
 
 

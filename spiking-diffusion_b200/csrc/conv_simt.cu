@@ -165,6 +165,94 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtParams p) {
   }
 }
 
+
+// Real-valued input and output, fp32 [T*B, C, H, W] (un-fused layer.Conv2d / ConvTranspose2d, the training-mode forward
+// and, as the adjoint convolution, the input gradient): implicit GEMM on CUDA cores, 64 output pixels x 64 output
+// channels per block, K = (tap, input channel) staged through shared memory in slices of 16, 4 x 4 outputs per
+// thread.  The accumulation order per output (tap-major, channel inner, one FMA chain) is the generic kernel's.
+__global__ void __launch_bounds__(256) conv_real_tiled_kernel(const SimtParams p) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ __align__(16) float As[BK][BM];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const sd_conv_desc& d = p.d;
+  const int Cin = d.C_in, Cout = d.C_out, taps = d.kh * d.kw;
+  const int Ktot = taps * Cin;
+  const int64_t plane_in = (int64_t)d.H_in * d.W_in, plane_out = (int64_t)d.H_out * d.W_out;
+  const int64_t M = (int64_t)d.T * d.B * plane_out;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  // this thread's pixel for the A loads
+  const int ml = tid & 63, kl = tid >> 6;   // kl in 0..3
+  const int64_t m_ld = m0 + ml;
+  const bool m_ok = m_ld < M;
+  int oy = 0, ox = 0;
+  int64_t img = 0;
+  if (m_ok) {
+    img = m_ld / plane_out;
+    const int pp = (int)(m_ld - img * plane_out);
+    oy = pp / d.W_out;
+    ox = pp - oy * d.W_out;
+  }
+  const float* xin = (const float*)p.in + img * Cin * plane_in;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < Ktot; k0 += BK) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kk = kl + 4 * j, k = k0 + kk;
+      float a = 0.f, b = 0.f;
+      if (k < Ktot) {
+        const int tap = k / Cin, ci = k - tap * Cin;
+        const int ky = tap / d.kw, kx = tap - ky * d.kw;
+        int iy, ix;
+        bool ok = m_ok;
+        if (d.transposed) {
+          const int ny = oy + d.pad - ky, nx = ox + d.pad - kx;
+          ok = ok && ny >= 0 && nx >= 0 && (ny % d.stride) == 0 && (nx % d.stride) == 0;
+          iy = ny / d.stride; ix = nx / d.stride;
+        } else {
+          iy = oy * d.stride - d.pad + ky; ix = ox * d.stride - d.pad + kx;
+        }
+        ok = ok && iy >= 0 && iy < d.H_in && ix >= 0 && ix < d.W_in;
+        if (ok) a = xin[(int64_t)ci * plane_in + (int64_t)iy * d.W_in + ix];
+        if (n0 + ml < Cout) b = p.w[(int64_t)k * Cout + n0 + ml];
+      }
+      As[kk][ml] = a;
+      Bs[kk][ml] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][tx * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][ty * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* outp = (float*)p.out;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + tx * 4 + i;
+    if (m >= M) continue;
+    const int64_t im = m / plane_out;
+    const int64_t pp = m - im * plane_out;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = n0 + ty * 4 + j;
+      if (co < Cout) outp[(im * Cout + co) * plane_out + pp] = fmaf(acc[i][j], p.scale[co], p.shift[co]);
+    }
+  }
+}
+
 // Real-valued input that is constant over T (enc.conv1, den.conv1, vq.poisson): the convolution is evaluated once
 // and the LIF runs on a constant current.  One thread = one output pixel x 8 output channels, so every timestep's
 // spikes leave as ONE 16-byte store into the STF plane, consecutive lanes -> consecutive rows (coalesced); the
@@ -635,6 +723,13 @@ int sd_conv_lif_simt(const sd_conv_desc* d, const sd_conv_args* a, void* stream)
     return SD_OK;
   }
   static const bool force_generic = getenv("SD_SIMT_GENERIC") != nullptr;   // debugging aid: exact-order generic kernel
+  if (!force_generic && d->in_kind == SD_IN_REAL_SEQ && d->out_kind == SD_OUT_REAL_SEQ) {
+    const int64_t M = (int64_t)d->T * d->B * d->H_out * d->W_out;
+    dim3 grid((unsigned)((M + 63) / 64), (unsigned)((d->C_out + 63) / 64));
+    conv_real_tiled_kernel<<<grid, 256, 0, st>>>(p);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+  }
   if (!force_generic && d->in_kind == SD_IN_STF && d->in_T == d->T && d->T <= 16 && d->out_kind == SD_OUT_MEMOUT_TANH &&
       d->C_out <= 4 && (int64_t)d->kh * d->kw * d->C_in * 4 * sizeof(float) <= 48 * 1024) {
     const int64_t npix = (int64_t)d->B * d->H_out * d->W_out;

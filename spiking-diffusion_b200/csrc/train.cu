@@ -1,64 +1,120 @@
-// Training-path kernels, first correct versions on CUDA cores:
+// Training-path kernels on CUDA cores (fp32, exact products):
 //   sd_conv_wgrad        weight / bias gradient of layer.Conv2d / layer.ConvTranspose2d in 'm' mode
 //   sd_bn_train_forward  train-mode BatchNorm2d (batch statistics over T*N*H*W)      SJ/activation_based/layer.py:458-465
 //   sd_bn_backward       its backward
 // The input gradient of a convolution is itself a (transposed) convolution and reuses conv_simt.cu.
-// These kernels are correctness-first (parity with torch autograd); they are not on the sampling hot path.
+// Parity target is torch autograd in fp32; they are not on the sampling hot path.
 #include "common.cuh"
 
 namespace sd {
 
-constexpr int kMaxTaps = 25;
+// Weight gradient as a tiled GEMM on CUDA cores.  With U the tensor that is gathered through the kernel window and V the
+// one on the anchor grid,
+//   conv      : U = x  (a = ci), V = gy (b = co), anchor = output pixel:  gw[co, ci, tap] = sum_p U[p + tap] V[p]
+//   transposed: U = gy (a = co), V = x  (b = ci), anchor = input pixel :  gw[ci, co, tap] = sum_p U[p + tap] V[p]
+// where "p + tap" is the position anchor * stride - pad + (ky, kx) on U's grid.  One block = 64 rows (tap, a) x 64
+// columns b, reduction over a slice of the n_outer * Ha * Wa anchor pixels (grid.z splits), 4 x 4 outputs per thread;
+// partial sums go to a [splits][rows][cols] workspace and a second kernel adds them in a fixed order (deterministic) and
+// scatters to the reference's parameter layout.
+constexpr int kWgBR = 64, kWgBC = 64, kWgBP = 16, kWgPad = 68;
 
-// One block per (co, ci): threads sweep (n, oy, ox), accumulate one partial sum per tap, block-reduce.
-//   conv      : gw[co,ci,ky,kx] = sum gy[n,co,oy,ox] * x[n,ci,oy*s-p+ky, ox*s-p+kx]
-//   transposed: gw[ci,co,ky,kx] = sum x[n,ci,iy,ix] * gy[n,co,iy*s-p+ky, ix*s-p+kx]
-__global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy,
-                                                         float* __restrict__ gw, sd_conv_desc d, int64_t n_outer) {
-  const int co = blockIdx.x / d.C_in, ci = blockIdx.x % d.C_in;
+__global__ void __launch_bounds__(256) conv_wgrad_tiled_kernel(const float* __restrict__ x, const float* __restrict__ gy,
+                                                               float* __restrict__ part, sd_conv_desc d, int64_t n_outer,
+                                                               int64_t p_per_split) {
+  __shared__ __align__(16) float Us[kWgBP][kWgPad];
+  __shared__ __align__(16) float Vs[kWgBP][kWgPad];
   const int taps = d.kh * d.kw;
-  float acc[kMaxTaps];
+  const int A = d.transposed ? d.C_out : d.C_in;    // channels of U
+  const int Bc = d.transposed ? d.C_in : d.C_out;   // channels of V
+  const float* U = d.transposed ? gy : x;
+  const float* V = d.transposed ? x : gy;
+  const int Ha = d.transposed ? d.H_in : d.H_out, Wa = d.transposed ? d.W_in : d.W_out;   // anchor grid (V)
+  const int Hu = d.transposed ? d.H_out : d.H_in, Wu = d.transposed ? d.W_out : d.W_in;   // gathered grid (U)
+  const int R = taps * A;
+  const int64_t P = n_outer * Ha * Wa;
+  const int r0 = blockIdx.x * kWgBR, c0 = blockIdx.y * kWgBC;
+  const int64_t p_begin = (int64_t)blockIdx.z * p_per_split;
+  const int64_t p_end = p_begin + p_per_split < P ? p_begin + p_per_split : P;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int pl = tid & 15, el = tid >> 4;   // load mapping: pixel fastest (coalesced along x), 16 rows / cols per pass
+  float acc[4][4];
 #pragma unroll
-  for (int k = 0; k < kMaxTaps; ++k) acc[k] = 0.f;
-  // the "anchor" grid is the conv output (conv) or the conv-transpose input (transposed)
-  const int Ha = d.transposed ? d.H_in : d.H_out, Wa = d.transposed ? d.W_in : d.W_out;
-  const int Hb = d.transposed ? d.H_out : d.H_in, Wb = d.transposed ? d.W_out : d.W_in;
-  const int64_t total = n_outer * Ha * Wa;
-  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
-    const int ax = (int)(i % Wa);
-    int64_t r = i / Wa;
-    const int ay = (int)(r % Ha);
-    const int64_t n = r / Ha;
-    // value on the anchor grid and plane on the other grid
-    const float va = d.transposed ? x[((n * d.C_in + ci) * Ha + ay) * Wa + ax] : gy[((n * d.C_out + co) * Ha + ay) * Wa + ax];
-    const float* pb = d.transposed ? gy + (n * d.C_out + co) * (int64_t)Hb * Wb : x + (n * d.C_in + ci) * (int64_t)Hb * Wb;
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int k = 0; k < kMaxTaps; ++k) {
-      if (k < taps) {
-        const int ky = k / d.kw, kx = k - ky * d.kw;
-        const int by = ay * d.stride - d.pad + ky, bx = ax * d.stride - d.pad + kx;
-        if (by >= 0 && by < Hb && bx >= 0 && bx < Wb) acc[k] = fmaf(va, pb[by * Wb + bx], acc[k]);
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // (tap, a) of the four U rows this thread loads
+  int r_a[4], r_ky[4], r_kx[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int r = r0 + el + 16 * j;
+    const int tap = r < R ? r / A : 0;
+    r_a[j] = r < R ? r - tap * A : -1;
+    r_ky[j] = tap / d.kw;
+    r_kx[j] = tap - r_ky[j] * d.kw;
+  }
+  for (int64_t pb = p_begin; pb < p_end; pb += kWgBP) {
+    const int64_t pidx = pb + pl;
+    const bool p_ok = pidx < p_end;
+    int64_t n = 0;
+    int ay = 0, ax = 0;
+    if (p_ok) {
+      n = pidx / ((int64_t)Ha * Wa);
+      const int pp = (int)(pidx - n * Ha * Wa);
+      ay = pp / Wa;
+      ax = pp - ay * Wa;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float u = 0.f, v = 0.f;
+      if (p_ok && r_a[j] >= 0) {
+        const int uy = ay * d.stride - d.pad + r_ky[j], ux = ax * d.stride - d.pad + r_kx[j];
+        if (uy >= 0 && uy < Hu && ux >= 0 && ux < Wu) u = U[((n * A + r_a[j]) * Hu + uy) * Wu + ux];
       }
+      const int c = c0 + el + 16 * j;
+      if (p_ok && c < Bc) v = V[((n * Bc + c) * Ha + ay) * Wa + ax];
+      Us[pl][el + 16 * j] = u;
+      Vs[pl][el + 16 * j] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int pp = 0; pp < kWgBP; ++pp) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&Us[pp][tx * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Vs[pp][ty * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* out = part + (int64_t)blockIdx.z * R * Bc;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + tx * 4 + i;
+    if (r >= R) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + ty * 4 + j;
+      if (c < Bc) out[(int64_t)r * Bc + c] = acc[i][j];
     }
   }
-  __shared__ float red[8][kMaxTaps];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < kMaxTaps; ++k) {
-    if (k < taps) {
-      float v = acc[k];
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-      if (lane == 0) red[warp][k] = v;
-    }
-  }
-  __syncthreads();
-  if ((int)threadIdx.x < taps) {
-    float v = 0.f;
-    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
-    const int64_t idx = d.transposed ? (((int64_t)ci * d.C_out + co) * taps + threadIdx.x)
-                                     : (((int64_t)co * d.C_in + ci) * taps + threadIdx.x);
-    gw[idx] = v;
+}
+
+// gw (reference layout) = sum over splits of part[split][(tap, a)][b]
+__global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ gw,
+                                                                sd_conv_desc d, int splits) {
+  const int taps = d.kh * d.kw;
+  const int A = d.transposed ? d.C_out : d.C_in, Bc = d.transposed ? d.C_in : d.C_out;
+  const int64_t total = (int64_t)taps * A * Bc;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(int64_t)z * total + i];
+    const int b = (int)(i % Bc);
+    const int64_t r = i / Bc;
+    const int a = (int)(r % A), tap = (int)(r / A);
+    // conv: a = ci, b = co -> gw[co][ci][tap];  transposed: a = co, b = ci -> gw[ci][co][tap]
+    gw[((int64_t)b * A + a) * taps + tap] = s;
   }
 }
 
@@ -168,16 +224,44 @@ using namespace sd;
 
 extern "C" {
 
+// reduction splits: enough blocks for two waves of the SMs, slices of at least 256 anchor pixels
+static int wgrad_splits(const sd_conv_desc* d) {
+  const int taps = d->kh * d->kw;
+  const int A = d->transposed ? d->C_out : d->C_in, Bc = d->transposed ? d->C_in : d->C_out;
+  const int64_t P = (int64_t)d->T * d->B * (d->transposed ? d->H_in * d->W_in : d->H_out * d->W_out);
+  const int64_t tiles = (int64_t)((taps * A + kWgBR - 1) / kWgBR) * ((Bc + kWgBC - 1) / kWgBC);
+  int64_t s = (2 * 148 + tiles - 1) / tiles;
+  const int64_t smax = P / 256 > 0 ? P / 256 : 1;
+  if (s > smax) s = smax;
+  if (s > 64) s = 64;
+  return (int)(s < 1 ? 1 : s);
+}
+
+int64_t sd_conv_wgrad_workspace_bytes(const sd_conv_desc* d) {
+  if (!d || validate_conv_desc(d) != SD_OK) return 0;
+  return (int64_t)wgrad_splits(d) * d->kh * d->kw * d->C_in * d->C_out * (int64_t)sizeof(float);
+}
+
 int sd_conv_wgrad(const sd_conv_desc* d, const float* x, const float* grad_out, float* grad_w, float* grad_bias,
-                  void* stream) {
+                  void* workspace, void* stream) {
   int rc = validate_conv_desc(d);
   if (rc) return rc;
-  SD_REQUIRE(d->kh * d->kw <= kMaxTaps, "conv_wgrad: kernel larger than 5x5 is not supported");
-  SD_REQUIRE(x && grad_out && grad_w, "null pointer argument");
+  SD_REQUIRE(x && grad_out && grad_w && workspace, "null pointer argument (workspace: sd_conv_wgrad_workspace_bytes)");
   SD_DEVICE_OR_RETURN();
   cudaStream_t st = as_stream(stream);
   const int64_t n_outer = (int64_t)d->T * d->B;
-  conv_wgrad_kernel<<<(unsigned)(d->C_out * d->C_in), 256, 0, st>>>(x, grad_out, grad_w, *d, n_outer);
+  const int taps = d->kh * d->kw;
+  const int A = d->transposed ? d->C_out : d->C_in, Bc = d->transposed ? d->C_in : d->C_out;
+  const int64_t P = n_outer * (d->transposed ? d->H_in * d->W_in : d->H_out * d->W_out);
+  const int splits = wgrad_splits(d);
+  int64_t per = (P + splits - 1) / splits;
+  per = (per + kWgBP - 1) / kWgBP * kWgBP;
+  dim3 grid((unsigned)((taps * A + kWgBR - 1) / kWgBR), (unsigned)((Bc + kWgBC - 1) / kWgBC), (unsigned)splits);
+  conv_wgrad_tiled_kernel<<<grid, 256, 0, st>>>(x, grad_out, (float*)workspace, *d, n_outer, per);
+  SD_LAUNCH_CHECK();
+  const int64_t total = (int64_t)taps * A * Bc;
+  conv_wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, st>>>(
+      (const float*)workspace, grad_w, *d, splits);
   SD_LAUNCH_CHECK();
   if (grad_bias) {
     channel_sum_kernel<<<(unsigned)d->C_out, 256, 0, st>>>(grad_out, grad_bias, n_outer, d->C_out,
