@@ -167,23 +167,25 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtParams p) {
 
 
 // Real-valued input and output, fp32 [T*B, C, H, W] (un-fused layer.Conv2d / ConvTranspose2d, the training-mode forward
-// and, as the adjoint convolution, the input gradient): implicit GEMM on CUDA cores, 64 output pixels x 64 output
-// channels per block, K = (tap, input channel) staged through shared memory in slices of 16, 4 x 4 outputs per
-// thread.  The accumulation order per output (tap-major, channel inner, one FMA chain) is the generic kernel's.
+// and, as the adjoint convolution, the input gradient): implicit GEMM on CUDA cores.  128 output pixels x 64 output
+// channels per block, 8 x 4 outputs per thread; K runs tap-major with 8 input channels per slice, so the window
+// geometry is evaluated once per tap and the inner loop has no integer division; the next slice is fetched into
+// registers while the current one is multiplied out of shared memory (two buffers, one barrier per slice).  The
+// accumulation order per output (tap-major, channel inner, one FMA chain) is the generic kernel's.
 __global__ void __launch_bounds__(256) conv_real_tiled_kernel(const SimtParams p) {
-  constexpr int BM = 64, BN = 64, BK = 16;
-  __shared__ __align__(16) float As[BK][BM];
-  __shared__ __align__(16) float Bs[BK][BN];
+  constexpr int BM = 128, BN = 64, BK = 8;
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
   const sd_conv_desc& d = p.d;
   const int Cin = d.C_in, Cout = d.C_out, taps = d.kh * d.kw;
-  const int Ktot = taps * Cin;
   const int64_t plane_in = (int64_t)d.H_in * d.W_in, plane_out = (int64_t)d.H_out * d.W_out;
   const int64_t M = (int64_t)d.T * d.B * plane_out;
   const int64_t m0 = (int64_t)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  // this thread's pixel for the A loads
-  const int ml = tid & 63, kl = tid >> 6;   // kl in 0..3
+  // load mapping: A pixel ml, channels kl + 2 j (j < 4); B column nl, channels kb + 4 j (j < 2)
+  const int ml = tid & 127, kl = tid >> 7;
+  const int nl = tid & 63, kb = tid >> 6;
   const int64_t m_ld = m0 + ml;
   const bool m_ok = m_ld < M;
   int oy = 0, ox = 0;
@@ -195,53 +197,83 @@ __global__ void __launch_bounds__(256) conv_real_tiled_kernel(const SimtParams p
     ox = pp - oy * d.W_out;
   }
   const float* xin = (const float*)p.in + img * Cin * plane_in;
-  float acc[4][4];
+  const bool n_ok = n0 + nl < Cout;
+  const int slices_per_tap = (Cin + BK - 1) / BK;
+  const int n_slices = taps * slices_per_tap;
+
+  float acc[8][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < Ktot; k0 += BK) {
+  // window geometry of this thread's load pixel for the current tap
+  int tap = 0, ci0 = 0;
+  const float* a_ptr = nullptr;   // x at (iy, ix) of channel 0, or null if the tap falls outside
+  auto set_tap = [&](int tp) {
+    const int ky = tp / d.kw, kx = tp - ky * d.kw;
+    int iy, ix;
+    bool ok = m_ok;
+    if (d.transposed) {
+      const int ny = oy + d.pad - ky, nx = ox + d.pad - kx;
+      ok = ok && ny >= 0 && nx >= 0 && (ny % d.stride) == 0 && (nx % d.stride) == 0;
+      iy = ny / d.stride; ix = nx / d.stride;
+    } else {
+      iy = oy * d.stride - d.pad + ky; ix = ox * d.stride - d.pad + kx;
+    }
+    ok = ok && iy >= 0 && iy < d.H_in && ix >= 0 && ix < d.W_in;
+    a_ptr = ok ? xin + (int64_t)iy * d.W_in + ix : nullptr;
+  };
+  float a_reg[4], b_reg[2];
+  auto fetch = [&]() {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int kk = kl + 4 * j, k = k0 + kk;
-      float a = 0.f, b = 0.f;
-      if (k < Ktot) {
-        const int tap = k / Cin, ci = k - tap * Cin;
-        const int ky = tap / d.kw, kx = tap - ky * d.kw;
-        int iy, ix;
-        bool ok = m_ok;
-        if (d.transposed) {
-          const int ny = oy + d.pad - ky, nx = ox + d.pad - kx;
-          ok = ok && ny >= 0 && nx >= 0 && (ny % d.stride) == 0 && (nx % d.stride) == 0;
-          iy = ny / d.stride; ix = nx / d.stride;
-        } else {
-          iy = oy * d.stride - d.pad + ky; ix = ox * d.stride - d.pad + kx;
-        }
-        ok = ok && iy >= 0 && iy < d.H_in && ix >= 0 && ix < d.W_in;
-        if (ok) a = xin[(int64_t)ci * plane_in + (int64_t)iy * d.W_in + ix];
-        if (n0 + ml < Cout) b = p.w[(int64_t)k * Cout + n0 + ml];
-      }
-      As[kk][ml] = a;
-      Bs[kk][ml] = b;
+      const int ci = ci0 + kl + 2 * j;
+      a_reg[j] = (a_ptr != nullptr && ci < Cin) ? a_ptr[(int64_t)ci * plane_in] : 0.f;
     }
-    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int ci = ci0 + kb + 4 * j;
+      b_reg[j] = (n_ok && ci < Cin) ? p.w[((int64_t)tap * Cin + ci) * Cout + n0 + nl] : 0.f;
+    }
+  };
+  auto stage = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) As[buf][kl + 2 * j][ml] = a_reg[j];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) Bs[buf][kb + 4 * j][nl] = b_reg[j];
+  };
+  auto advance = [&]() {
+    ci0 += BK;
+    if (ci0 >= Cin) { ci0 = 0; ++tap; if (tap < taps) set_tap(tap); }
+  };
+  set_tap(0);
+  fetch();
+  stage(0);
+  advance();
+  __syncthreads();
+  for (int sidx = 0; sidx < n_slices; ++sidx) {
+    const int buf = sidx & 1;
+    const bool more = sidx + 1 < n_slices;
+    if (more) fetch();
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][tx * 4]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][ty * 4]);
-      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][tx * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + tx * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][kk][ty * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
+    if (more) { stage(buf ^ 1); advance(); }
     __syncthreads();
   }
   float* outp = (float*)p.out;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t m = m0 + tx * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + (i < 4 ? tx * 4 + i : 64 + tx * 4 + (i - 4));
     if (m >= M) continue;
     const int64_t im = m / plane_out;
     const int64_t pp = m - im * plane_out;
@@ -725,7 +757,7 @@ int sd_conv_lif_simt(const sd_conv_desc* d, const sd_conv_args* a, void* stream)
   static const bool force_generic = getenv("SD_SIMT_GENERIC") != nullptr;   // debugging aid: exact-order generic kernel
   if (!force_generic && d->in_kind == SD_IN_REAL_SEQ && d->out_kind == SD_OUT_REAL_SEQ) {
     const int64_t M = (int64_t)d->T * d->B * d->H_out * d->W_out;
-    dim3 grid((unsigned)((M + 63) / 64), (unsigned)((d->C_out + 63) / 64));
+    dim3 grid((unsigned)((M + 127) / 128), (unsigned)((d->C_out + 63) / 64));
     conv_real_tiled_kernel<<<grid, 256, 0, st>>>(p);
     SD_LAUNCH_CHECK();
     return SD_OK;

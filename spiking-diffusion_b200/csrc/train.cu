@@ -21,8 +21,8 @@ constexpr int kWgBR = 64, kWgBC = 64, kWgBP = 16, kWgPad = 68;
 __global__ void __launch_bounds__(256) conv_wgrad_tiled_kernel(const float* __restrict__ x, const float* __restrict__ gy,
                                                                float* __restrict__ part, sd_conv_desc d, int64_t n_outer,
                                                                int64_t p_per_split) {
-  __shared__ __align__(16) float Us[kWgBP][kWgPad];
-  __shared__ __align__(16) float Vs[kWgBP][kWgPad];
+  __shared__ __align__(16) float Us[2][kWgBP][kWgPad];
+  __shared__ __align__(16) float Vs[2][kWgBP][kWgPad];
   const int taps = d.kh * d.kw;
   const int A = d.transposed ? d.C_out : d.C_in;    // channels of U
   const int Bc = d.transposed ? d.C_in : d.C_out;   // channels of V
@@ -52,7 +52,9 @@ __global__ void __launch_bounds__(256) conv_wgrad_tiled_kernel(const float* __re
     r_ky[j] = tap / d.kw;
     r_kx[j] = tap - r_ky[j] * d.kw;
   }
-  for (int64_t pb = p_begin; pb < p_end; pb += kWgBP) {
+  // the next slice of 16 anchor pixels is fetched into registers while the current one is multiplied
+  float u_reg[4], v_reg[4];
+  auto fetch = [&](int64_t pb) {
     const int64_t pidx = pb + pl;
     const bool p_ok = pidx < p_end;
     int64_t n = 0;
@@ -72,20 +74,37 @@ __global__ void __launch_bounds__(256) conv_wgrad_tiled_kernel(const float* __re
       }
       const int c = c0 + el + 16 * j;
       if (p_ok && c < Bc) v = V[((n * Bc + c) * Ha + ay) * Wa + ax];
-      Us[pl][el + 16 * j] = u;
-      Vs[pl][el + 16 * j] = v;
+      u_reg[j] = u;
+      v_reg[j] = v;
     }
-    __syncthreads();
+  };
+  auto stage = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      Us[buf][pl][el + 16 * j] = u_reg[j];
+      Vs[buf][pl][el + 16 * j] = v_reg[j];
+    }
+  };
+  if (p_begin < p_end) {
+    fetch(p_begin);
+    stage(0);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int64_t pb = p_begin; pb < p_end; pb += kWgBP, buf ^= 1) {
+    const bool more = pb + kWgBP < p_end;
+    if (more) fetch(pb + kWgBP);
 #pragma unroll
     for (int pp = 0; pp < kWgBP; ++pp) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&Us[pp][tx * 4]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&Vs[pp][ty * 4]);
+      const float4 a4 = *reinterpret_cast<const float4*>(&Us[buf][pp][tx * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Vs[buf][pp][ty * 4]);
       const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
+    if (more) stage(buf ^ 1);
     __syncthreads();
   }
   float* out = part + (int64_t)blockIdx.z * R * Bc;
