@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
   auto b_empty = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + kMaxBStages + s); };
   auto acc_full = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages + s); };
   auto acc_empty = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages + 2 + s); };
+  // 16-byte aligned (tcgen05.alloc traps on a misaligned destination); both CTAs of a pair pass the same offset
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxAStages + 2 * kMaxBStages + 4));
   // pair only: "the peer's stage has landed" barriers in the leader, arrived remotely by the peer's relay warp
   auto a_full_peer = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages + 6 + s); };
@@ -761,6 +762,9 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
   c->b_stages = (int)(left / c->b_stage_bytes);
   if (c->b_stages > kMaxBStages) c->b_stages = kMaxBStages;
   c->smem_bytes = 1024 + c->a_stages * c->a_stage_bytes + c->b_stages * c->b_stage_bytes;
+  // every CTA allocates all 512 TMEM columns: ask for more than half of the SM's shared memory so that two CTAs of
+  // this kernel are never co-resident (the second would only sit in tcgen05.alloc until the first one exits)
+  if (c->smem_bytes < 117u * 1024u) c->smem_bytes = 117u * 1024u;
   c->n_tiles = (d->C_out + n_tile - 1) / n_tile;
   const int64_t R = (int64_t)d->B * d->H_in * d->W_in;
   c->m_tiles = (int)((R + kTileRows - 1) / kTileRows);

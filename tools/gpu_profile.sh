@@ -3,7 +3,7 @@
 # The sampler runs un-graphed here (ncu serialises kernels anyway); sub-batch plan and kernels are the bench defaults.
 mkdir -p gpurun_out
 export SD_SAMPLER_GRAPH=0
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 800 -c 800 --csv --log-file gpurun_out/p_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/p_list.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1990 -c 2100 --csv --log-file gpurun_out/p_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/p_list.log 2>&1
 # one diffusion step of every sub-batch: 5 tcgen05 layers x 5 sub-batches, in launch order (sub-batch major)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc -s 50 -c 25 -o gpurun_out/p_conv_tc python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/p_tc.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:sample_step -s 10 -c 1 -o gpurun_out/p_sample python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/p_sample.log 2>&1

@@ -74,7 +74,12 @@ def summarize_launches(csvf, out, title):
             f.write(f"{k:44s} {len(v):8d} {sum(v):11.1f} {sum(v) / len(v):9.2f} {100 * sum(v) / tot:6.1f}%\n")
         f.write(f"{'TOTAL':44s} {sum(len(v) for v in agg.values()):8d} {tot:11.1f}\n\n# one diffusion step, in launch order:\n")
         start = next((i for i, s in enumerate(seq) if s[0].startswith("denoiser_input")), 0)
-        for name, grid, v in seq[start:start + 16]:
+        f.write("# (sub-batch 0 of 5; the other sub-batches follow in the same order)\n")
+        for name, grid, v in seq[start:start + 8]:
+            f.write(f"  {name:44s} grid {grid:14s} {v:9.2f} us\n")
+        first_dec = next((i for i, s in enumerate(seq) if s[0].startswith("vq_gather")), None)
+        f.write("\n# decode after the last diffusion step, in launch order:\n")
+        for name, grid, v in ([] if first_dec is None else seq[first_dec:first_dec + 8]):
             f.write(f"  {name:44s} grid {grid:14s} {v:9.2f} us\n")
     print("wrote", out)
 

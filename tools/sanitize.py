@@ -1,4 +1,5 @@
-"""Small end-to-end pass for compute-sanitizer (memcheck / racecheck / synccheck) on the GPU box."""
+"""Small end-to-end pass for compute-sanitizer (memcheck / racecheck / synccheck) on the GPU box: every kernel family
+of the library is launched at least once."""
 import os
 import sys
 
@@ -30,5 +31,20 @@ functional.set_step_mode(den8, "m")
 den8.load_state_dict(synth.synth_denoiser_state(0))
 den8 = den8.eval().cuda()
 lg = den8(torch.full((2, 1, 7, 7), float(K), device="cuda"), torch.ones(2, dtype=torch.long, device="cuda"))
+# CTA-pair kernel with two concurrent sub-batch streams (70 images -> 36 + 34), fused VQ-VAE plan (tensor-core
+# encoder / decoder routes), and one training iteration of each model (tiled conv / weight-gradient / BN / LIF backward)
+ab70 = AbsorbingDiffusion(den, mask_id=K, shape=(7, 7), n_samples=70)
+tok70 = ab70.sample(temp=1.0, sample_steps=2, seed=1)
+plan = vae.plan(T, 5, 28, 28)
+plan.forward(synth.synth_images(1, 5).cuda(), const_over_T=True)
+vae.train(); den.train()
+vae.data_variance = torch.tensor(0.09)
+img2 = synth.synth_images(2, 4).cuda()
+e_q, r_l, _ = vae(img2.unsqueeze(0).repeat(T, 1, 1, 1, 1), img2)
+(e_q + r_l).backward()
+functional.reset_net(vae)
+lg_t = den(torch.randint(0, K + 1, (4, 1, 7, 7)).float().cuda(), torch.randint(1, 50, (4,)).cuda())
+lg_t.square().mean().backward()
+functional.reset_net(den)
 torch.cuda.synchronize()
 print("sanitize pass done", float(rec.abs().max()), int(tok.max()), float(pred.abs().max()), float(lg.abs().max()))
