@@ -2,7 +2,9 @@
 //
 // Replaces layer.Conv2d -> layer.BatchNorm2d -> neuron.LIFNode for the spike->spike layers of the denoiser
 // (R/snn_model/vq_diffusion.py:165-187 via SJ/activation_based/layer.py:164-173,458-465 and neuron.py:799-809),
-// which carry >99.9 % of the sampling FLOPs.
+// which carry >99.9 % of the sampling FLOPs.  The stride-2 layers of the VQ-VAE use it too: the
+// transposed convolutions of the decoder as 3x3 convolutions of zero-inserted spikes (sd_stf_upsample2x) and enc.conv2 at
+// stride 1 followed by sd_stf_subsample2x (engine._UpsampledConvT / _Stride1Conv).
 //
 // GEMM view.  Activations live in the STF layout (include/sd_b200.h): per timestep and per 8-channel chunk a
 // plane of 16-byte rows, rows = the pixels of all images flattened densely (H*W rows per image, no padding).  For
@@ -652,7 +654,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
 // Configuration (shared by weight packing and launch)
 // ---------------------------------------------------------------------------------------------------
 // Experiment knobs (SD_TC_*) are read from the environment on every call: they are only consulted while a plan is
-// being built (weight packing) and at launch, where they must agree, and getenv is ~100 ns.
+// being built (weight packing) and at launch, where they must agree, and getenv is ~100 ns.  Defaults are the measured
+// best (profiles/r01_experiments.md); none of them changes results except through fp32 summation order (KBLK):
+//   SD_TC_PAIR=0            single-CTA kernel instead of 2-CTA pairs
+//   SD_TC_SMALL_BATCH_SPLIT=0  keep N = 128 for a lone small batch
+//   SD_TC_TCHUNK=0 / SD_TC_TACC=n   one pass over all T / n timesteps per pass (n = 2: two TMEM stages)
+//   SD_TC_N256, SD_TC_WIDE256       N = 256 tiles with 2 timesteps per pass
+//   SD_TC_NTILE, SD_TC_KBLK, SD_TC_ACC_STAGES, SD_TC_ALIGN   tile shape overrides
+//   SD_TC_PERSIST=0         one work unit per CTA / cluster
+//   SD_TC_DBG (with sd_debug_tc_trace)   1: skip spike stores, 2: skip TMEM loads (timing experiments only)
 static int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return s ? atoi(s) : dflt;
