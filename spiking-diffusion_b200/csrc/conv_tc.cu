@@ -60,6 +60,9 @@ struct TcConfig {
   int n_tchunks;   // passes per tile: T / T_acc.  T = 8 / 16 run as 2 / 4 passes of 4 timesteps at N = 128 with the
                    // membrane potential carried between passes in an L2-resident fp32 plane, instead of one pass at
                    // N = 64 / 32 (whose A-operand fetch per MMA is amortised over too few columns)
+  int tpar;        // 1: T-parallel small-batch mode.  Every (tile, pass) is an independent work unit whose epilogue writes
+                   // the BN-affined input currents (fp32) to the workspace; a second, bandwidth-bound kernel runs the LIF
+                   // recurrence over all T.  Used when a multi-pass layer would otherwise occupy a fraction of the SMs.
   int N_TILE;
   int KBLK;        // input channels per K block
   int acc_stages;
@@ -81,6 +84,7 @@ struct TcParams {
   __half* out_spk;
   __half* out_sum;
   float* out_real;
+  float* cur;               // tpar mode: currents [T][C_out/8][R_alloc][8] fp32 (workspace)
   float* v;                 // state plane (caller's LIF state or workspace), or null
   int v_load_initial;       // first pass starts from *v (else from v_reset)
   int v_store_final;        // last pass writes v back
@@ -304,8 +308,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
   // work units: (M tile, N tile) per CTA, or (pair of M tiles, N tile) per cluster
   const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int unit_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int total_tiles = (PAIR ? (c.m_tiles + 1) / 2 : c.m_tiles) * c.n_tiles;
-  auto m_tile_of = [&](int unit) { return PAIR ? 2 * (unit / c.n_tiles) + (int)cta_rank : unit / c.n_tiles; };
+  // In T-parallel mode a unit is one (tile, pass); otherwise a unit is a tile and its passes run back to back.
+  const int unit_passes = c.tpar ? 1 : c.n_tchunks;
+  const int total_tiles = (PAIR ? (c.m_tiles + 1) / 2 : c.m_tiles) * c.n_tiles * (c.tpar ? c.n_tchunks : 1);
+  auto tile_of = [&](int unit) { return c.tpar ? unit / c.n_tchunks : unit; };
+  auto pass0_of = [&](int unit) { return c.tpar ? unit % c.n_tchunks : 0; };
+  auto m_tile_of = [&](int unit) {
+    const int tl = tile_of(unit);
+    return PAIR ? 2 * (tl / c.n_tiles) + (int)cta_rank : tl / c.n_tiles;
+  };
   const int chunks = c.KBLK >> 3;            // 8-channel chunks per K block
   const uint32_t plane_bytes = (uint32_t)c.rows_ld * 16u;
 
@@ -317,8 +328,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
       // an odd number of M tiles leaves the last pair with a phantom second tile: it re-reads the last real tile (its
       // epilogue writes nothing because its rows are >= R_valid)
       const int64_t row0 = (int64_t)min(m_tile_of(tile), c.m_tiles - 1) * kTileRows;
-      for (int kbi = 0; kbi < c.num_kblocks * c.n_tchunks; ++kbi) {
-        const int tch = kbi / c.num_kblocks, kb = kbi - tch * c.num_kblocks;
+      for (int kbi = 0; kbi < c.num_kblocks * unit_passes; ++kbi) {
+        const int kb = kbi % c.num_kblocks, tch = pass0_of(tile) + kbi / c.num_kblocks;
         if (lane == 0) {
           mbar_wait(a_empty(st.stage), st.phase ^ 1);
           mbar_expect_tx(a_full(st.stage), c.a_stage_bytes);
@@ -345,9 +356,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     const int64_t stage_halfs = c.b_stage_bytes / 2;
     const int halves = PAIR ? 2 : 1;                 // pair: each CTA stages its own half (N/2 rows) of every B block
     for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
-      const int n_tile = tile % c.n_tiles;
+      const int n_tile = tile_of(tile) % c.n_tiles;
       const __half* wsrc = p.wpack + (int64_t)n_tile * c.num_kblocks * 9 * stage_halfs * halves + (int64_t)cta_rank * stage_halfs;
-      for (int itt = 0; itt < c.num_kblocks * 9 * c.n_tchunks; ++itt) {
+      for (int itt = 0; itt < c.num_kblocks * 9 * unit_passes; ++itt) {
         const int it = itt % (c.num_kblocks * 9);      // every T pass streams the same weights again
         const int kb = it / 9, tap = tap_order(it - kb * 9);
         mbar_wait(b_empty(st.stage), st.phase ^ 1);
@@ -364,7 +375,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     // ===== relay (peer CTA): tell the leader's MMA warp when this CTA's stages have landed, in consumption order =====
     PipeState sa, sb;
     for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
-      for (int kbi = 0; kbi < c.num_kblocks * c.n_tchunks; ++kbi) {
+      for (int kbi = 0; kbi < c.num_kblocks * unit_passes; ++kbi) {
         mbar_wait(a_full(sa.stage), sa.phase);
         if (lane == 0) mbar_arrive_remote(a_full_peer(sa.stage), 0);
         __syncwarp();
@@ -393,7 +404,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     // one iteration per (tile, T pass)
     int trace_it = 0;
     for (int tile = unit0, tch = 0; tile < total_tiles;
-         (++tch == c.n_tchunks) ? (tch = 0, tile += unit_stride) : 0) {
+         (++tch == unit_passes) ? (tch = 0, tile += unit_stride) : 0) {
       long long stall = 0;
       // rows of this tile on the top / bottom / left / right border of their image: the taps that would read across
       // that border have these output rows disabled.  Computed before the accumulator wait, so it overlaps the
@@ -488,10 +499,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     const float inv_tau = 1.0f / p.tau;
     const bool fast_lif = tau_pow2 && p.hard_reset && p.v_reset == 0.f;
     int trace_it = 0;
-    for (int tile = unit0, tch = 0; tile < total_tiles;
-         (++tch == c.n_tchunks) ? (tch = 0, tile += unit_stride) : 0) {
+    for (int tile = unit0, pass = 0; tile < total_tiles;
+         (++pass == unit_passes) ? (pass = 0, tile += unit_stride) : 0) {
+      const int tch = pass0_of(tile) + pass;
       const bool first_pass = tch == 0, last_pass = tch == c.n_tchunks - 1;
-      const int n0 = (tile % c.n_tiles) * c.N_TILE;
+      const int n0 = (tile_of(tile) % c.n_tiles) * c.N_TILE;
       const int64_t r = (int64_t)m_tile_of(tile) * kTileRows + q * 32 + lane;  // row (without guard)
       const int pp = (int)(r % p.P);
       const int py = pp / p.W, px = pp - py * p.W;
@@ -511,7 +523,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
           sc_[j] = a.x; sc_[j + 1] = a.y; sc_[j + 2] = a.z; sc_[j + 3] = a.w;
           sh_[j] = b.x; sh_[j + 1] = b.y; sh_[j + 2] = b.z; sh_[j + 3] = b.w;
         }
-        if (p.out_kind == SD_OUT_LIF) {
+        if (c.tpar) {
+          // T-parallel mode: this pass only delivers the input currents x[t] = conv * scale + shift of its timesteps
+          for (int tl = 0; tl < c.T_acc; ++tl) {
+            uint32_t acc[16];
+            tc_ld16(t_base + (uint32_t)(tl * c.N_TILE + cc), acc);
+            tc_ld_wait_on(acc);
+            if (valid) {
+              const int t = tch * c.T_acc + tl;
+              float* o = p.cur + (((int64_t)t * p.Cout8 + (n >> 3)) * p.R_alloc + p.G + r) * 8;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                float4 lo, hi;
+                lo.x = fmaf(__uint_as_float(acc[8 * h + 0]), sc_[8 * h + 0], sh_[8 * h + 0]);
+                lo.y = fmaf(__uint_as_float(acc[8 * h + 1]), sc_[8 * h + 1], sh_[8 * h + 1]);
+                lo.z = fmaf(__uint_as_float(acc[8 * h + 2]), sc_[8 * h + 2], sh_[8 * h + 2]);
+                lo.w = fmaf(__uint_as_float(acc[8 * h + 3]), sc_[8 * h + 3], sh_[8 * h + 3]);
+                hi.x = fmaf(__uint_as_float(acc[8 * h + 4]), sc_[8 * h + 4], sh_[8 * h + 4]);
+                hi.y = fmaf(__uint_as_float(acc[8 * h + 5]), sc_[8 * h + 5], sh_[8 * h + 5]);
+                hi.z = fmaf(__uint_as_float(acc[8 * h + 6]), sc_[8 * h + 6], sh_[8 * h + 6]);
+                hi.w = fmaf(__uint_as_float(acc[8 * h + 7]), sc_[8 * h + 7], sh_[8 * h + 7]);
+                *reinterpret_cast<float4*>(o + (int64_t)h * p.R_alloc * 8) = lo;
+                *reinterpret_cast<float4*>(o + (int64_t)h * p.R_alloc * 8 + 4) = hi;
+              }
+            }
+          }
+        } else if (p.out_kind == SD_OUT_LIF) {
           float v[16];
           __half2 cnt2[8];   // spike counts so far (exact in fp16: at most T <= 16)
           const bool want_sum = p.out_sum != nullptr;
@@ -650,6 +687,70 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
   }
 }
 
+// Second kernel of the T-parallel mode: the LIF recurrence over all T on the currents written by the convolution
+// passes.  One thread = one pixel row x 8 channels (32-byte current loads, 16-byte spike stores, lanes on consecutive
+// rows); the arithmetic is the fused epilogue's, so both modes produce the same bits.
+__global__ void __launch_bounds__(256) lif_from_currents_kernel(const TcParams p) {
+  int tau_exp;
+  const bool tau_pow2 = frexpf(p.tau, &tau_exp) == 0.5f;
+  const float inv_tau = 1.0f / p.tau;
+  const bool fast_lif = tau_pow2 && p.hard_reset && p.v_reset == 0.f;
+  const int64_t total = (int64_t)p.Cout8 * p.R_valid;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ch = i / p.R_valid, r = i - ch * p.R_valid;
+    const int64_t off = (ch * p.R_alloc + p.G + r) * 8;
+    float v[8];
+    if (p.v != nullptr && p.v_load_initial) {
+      const float4 a = *reinterpret_cast<const float4*>(p.v + off), b = *reinterpret_cast<const float4*>(p.v + off + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = p.hard_reset ? p.v_reset : 0.f;
+    }
+    __half2 cnt2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cnt2[k] = __floats2half2_rn(0.f, 0.f);
+    for (int t = 0; t < p.T; ++t) {
+      const float* cp = p.cur + (int64_t)t * p.Cout8 * p.R_alloc * 8 + off;
+      const float4 a = *reinterpret_cast<const float4*>(cp), b = *reinterpret_cast<const float4*>(cp + 4);
+      const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      uint32_t packed[4];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        float sf[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (fast_lif) {
+            const float h = fmaf(__fsub_rn(x[j + u], v[j + u]), inv_tau, v[j + u]);
+            sf[u] = h >= p.v_th ? 1.f : 0.f;
+            v[j + u] = fmaf(-h, sf[u], h);
+          } else {
+            const float dv = p.hard_reset ? __fsub_rn(x[j + u], __fsub_rn(v[j + u], p.v_reset)) : __fsub_rn(x[j + u], v[j + u]);
+            const float h = __fadd_rn(v[j + u], tau_pow2 ? __fmul_rn(dv, inv_tau) : __fdiv_rn(dv, p.tau));
+            const bool s = h >= p.v_th;
+            sf[u] = s ? 1.f : 0.f;
+            v[j + u] = p.hard_reset ? (s ? p.v_reset : h) : (s ? __fsub_rn(h, p.v_th) : h);
+          }
+        }
+        const __half2 s2 = __floats2half2_rn(sf[0], sf[1]);
+        packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&s2);
+        cnt2[j >> 1] = __hadd2(cnt2[j >> 1], s2);
+      }
+      if (p.out_spk != nullptr)
+        *reinterpret_cast<uint4*>(p.out_spk + (int64_t)t * p.Cout8 * p.R_alloc * 8 + off) =
+            make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+    if (p.out_sum != nullptr) {
+      const uint32_t* pk = reinterpret_cast<const uint32_t*>(cnt2);
+      *reinterpret_cast<uint4*>(p.out_sum + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    if (p.v != nullptr && p.v_store_final) {
+      *reinterpret_cast<float4*>(p.v + off) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(p.v + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Configuration (shared by weight packing and launch)
 // ---------------------------------------------------------------------------------------------------
@@ -720,6 +821,21 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
     while (n_tile > 32 && env_int("SD_TC_SMALL_BATCH_SPLIT", 1) &&
            (int64_t)m_tiles * ((d->C_out + n_tile - 1) / n_tile) * 2 * conc <= sms && d->C_out > n_tile / 2)
       n_tile /= 2;
+  }
+  // T-parallel small-batch mode: a multi-pass layer whose full-size (N = 128, paired) tiles would occupy less than
+  // half of the clusters runs its passes as independent work units (x T/4 parallelism at full tile efficiency) and
+  // leaves the LIF recurrence to a second kernel.  The per-CTA K loop, which bounds a small batch, gets T/4 x shorter.
+  c->tpar = 0;
+  if (d->out_kind == SD_OUT_LIF && c->n_tchunks > 1 && d->concurrent <= 1 && env_int("SD_TC_TPAR", 1)) {
+    check_device();
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const int64_t rows = (int64_t)d->B * d->H_in * d->W_in;
+    const int64_t m_tiles = (rows + kTileRows - 1) / kTileRows;
+    const int64_t pair_units = ((m_tiles + 1) / 2) * ((d->C_out + 127) / 128);
+    if (pair_units * 4 <= sms && c->T_acc * 128 <= 512) {
+      c->tpar = 1;
+      n_tile = 128;
+    }
   }
   n_tile = env_int("SD_TC_NTILE", n_tile);
   while (n_tile > 32 && n_tile / 2 >= d->C_out) n_tile /= 2;
@@ -866,8 +982,9 @@ int64_t sd_conv_workspace_bytes(const sd_conv_desc* d) {
   TcConfig c;
   if (!d || validate_conv_desc(d) != SD_OK || tc_config(d, &c) != SD_OK) return 0;
   if (c.n_tchunks <= 1) return 0;
-  // one fp32 state plane [C_out/8][R_alloc][8]
-  return (int64_t)c8(d->C_out) * stf_rows(d->B, d->H_out, d->W_out) * 8 * (int64_t)sizeof(float);
+  // one fp32 state plane [C_out/8][R_alloc][8]; in T-parallel mode one plane of currents per timestep instead
+  const int64_t plane = (int64_t)c8(d->C_out) * stf_rows(d->B, d->H_out, d->W_out) * 8 * (int64_t)sizeof(float);
+  return c.tpar ? plane * d->T : plane;
 }
 
 int64_t sd_conv_weight_layout_tc(const sd_conv_desc* d) {
@@ -927,7 +1044,12 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
   p.v = a->v ? a->v : (float*)a->workspace;
   p.v_load_initial = a->v != nullptr;
   p.v_store_final = a->v != nullptr;
-  if (c.n_tchunks > 1 && p.v == nullptr) {
+  if (c.tpar) {
+    SD_REQUIRE(a->workspace != nullptr, "conv_tc: this configuration needs args.workspace (sd_conv_workspace_bytes)");
+    p.cur = (float*)a->workspace;
+    p.v = a->v;
+  }
+  if (c.n_tchunks > 1 && !c.tpar && p.v == nullptr) {
     set_error("conv_tc: T=%d runs as %d passes and needs args.v or args.workspace (sd_conv_workspace_bytes)", d->T,
               c.n_tchunks);
     return SD_ERR_INVALID;
@@ -949,11 +1071,12 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
   cudaStream_t st = as_stream(stream);
   int grid;
   const bool persist = env_int("SD_TC_PERSIST", 1) != 0;   // experiment knob: 0 = one work unit per CTA / cluster
+  const int unit_mult = c.tpar ? c.n_tchunks : 1;
   if (c.pair) {
-    const int units = ((c.m_tiles + 1) / 2) * c.n_tiles;
+    const int units = ((c.m_tiles + 1) / 2) * c.n_tiles * unit_mult;
     grid = 2 * (units < sm_count() / 2 || !persist ? units : sm_count() / 2);
   } else {
-    grid = c.m_tiles * c.n_tiles;
+    grid = c.m_tiles * c.n_tiles * unit_mult;
     if (grid > sm_count() && persist) grid = sm_count();
   }
 #define SD_TC_LAUNCH_ONE(NS, KS, PR)                                                                               \
@@ -993,6 +1116,13 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
 #undef SD_TC_LAUNCH
 #undef SD_TC_LAUNCH_ONE
   SD_LAUNCH_CHECK();
+  if (c.tpar) {
+    const int64_t n = (int64_t)p.Cout8 * p.R_valid;
+    int64_t bl = (n + 255) / 256;
+    if (bl > (int64_t)sm_count() * 8) bl = (int64_t)sm_count() * 8;
+    lif_from_currents_kernel<<<(unsigned)bl, 256, 0, st>>>(p);
+    SD_LAUNCH_CHECK();
+  }
   return SD_OK;
 }
 
