@@ -818,7 +818,11 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
     const int64_t rows = (int64_t)d->B * d->H_in * d->W_in;
     const int m_tiles = (int)((rows + kTileRows - 1) / kTileRows);
     const int conc = d->concurrent > 1 ? d->concurrent : 1;   // sub-batches on other streams fill the SMs instead
-    while (n_tile > 32 && env_int("SD_TC_SMALL_BATCH_SPLIT", 1) &&
+    // Only when the tiles cannot be paired (a single M tile): the cycle-stamp trace shows that an un-paired MMA costs
+    // 72-79 cycles whatever N is (the fetch of the row-shifted A rows dominates) while a paired N = 128 MMA does 8x the
+    // work of an N = 32 one in 64 cycles, and the K loop per CTA - the critical path of a small batch - is the same.
+    const bool can_pair = env_int("SD_TC_PAIR", 1) && m_tiles >= 2 && n_tile == 128;
+    while (n_tile > 32 && env_int("SD_TC_SMALL_BATCH_SPLIT", 1) && !can_pair &&
            (int64_t)m_tiles * ((d->C_out + n_tile - 1) / n_tile) * 2 * conc <= sms && d->C_out > n_tile / 2)
       n_tile /= 2;
   }
