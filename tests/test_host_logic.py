@@ -161,7 +161,7 @@ def test_tc_weight_layout_key_depends_on_tiles_not_on_concurrent_sub_batches():
     assert key(52, 5) == full                              # a concurrent sub-batch keeps the full-size tiles
     assert key(52, 1) == full                              # pairable tiles are never narrowed (an un-paired MMA costs
     assert key(1024, 1) == full                            # the same whatever N is)
-    lone, shared = key(2, 1), key(2, 8)                    # a single M tile cannot be paired
+    lone, shared = key(2, 1), key(2, 64)                   # a single M tile cannot be paired
     assert lone & 1 == 0 and shared & 1 == 0
     assert (lone >> 16) < 128 and (shared >> 16) == 128    # alone it is cut into narrower N tiles, concurrent it is not
     bad = _lib.ConvDesc()
