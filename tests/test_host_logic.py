@@ -166,3 +166,30 @@ def test_tc_weight_layout_key_depends_on_tiles_not_on_concurrent_sub_batches():
     assert (lone >> 16) < 128 and (shared >> 16) == 128    # alone it is cut into narrower N tiles, concurrent it is not
     bad = _lib.ConvDesc()
     assert L.sd_conv_weight_layout_tc(ctypes.byref(bad)) == -1
+
+
+def test_strided_layers_restated_for_the_tensor_core_kernel_are_identities():
+    """The two algebraic restatements behind the tcgen05 VQ-VAE routes, checked with torch on the CPU:
+    ConvTranspose2d(k3, s2, p1, op1) == Conv2d(k3, s1, p1) with transposed + flipped taps on the zero-inserted input;
+    Conv2d(k3, s2, p1) == the even positions of Conv2d(k3, s1, p1)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    for H, W in ((7, 7), (8, 5)):
+        convt = torch.nn.ConvTranspose2d(16, 32, 3, stride=2, padding=1, output_padding=1)
+        assert engine._UpsampledConvT.eligible(convt)
+        shim = engine._UpsampledConvT(convt)
+        x = (torch.rand(3, 16, H, W, generator=g) < 0.3).float()
+        up = torch.zeros(3, 16, 2 * H, 2 * W)
+        up[..., ::2, ::2] = x
+        ref = convt(x)
+        got = F.conv2d(up, shim.weight, convt.bias, stride=1, padding=1)
+        assert got.shape == ref.shape and float((got - ref).abs().max()) <= 1e-5
+        conv = torch.nn.Conv2d(16, 32, 3, stride=2, padding=1)
+        assert engine._Stride1Conv.eligible(conv)
+        s1 = engine._Stride1Conv(conv)
+        ref2 = conv(x)
+        got2 = F.conv2d(x, s1.weight, s1.bias, stride=1, padding=1)[..., ::2, ::2]
+        assert got2.shape == ref2.shape and float((got2 - ref2).abs().max()) <= 1e-5
+    assert not engine._UpsampledConvT.eligible(torch.nn.ConvTranspose2d(16, 32, 3, stride=1, padding=1))
+    assert not engine._UpsampledConvT.eligible(torch.nn.ConvTranspose2d(16, 3, 3, stride=2, padding=1, output_padding=1))
+    assert not engine._Stride1Conv.eligible(torch.nn.Conv2d(1, 32, 3, stride=2, padding=1))
