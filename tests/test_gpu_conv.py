@@ -309,3 +309,28 @@ def test_fused_layer_with_general_lif_parameters(impl, tau, v_th, v_reset):
     _lib.check(_lib.lib().sd_state_convert(_lib.ptr(v), _lib.ptr(v_got), B, cout, H, H, 0, _lib.stream_ptr()))
     same = (got.cpu() == s_ref).all(dim=0)
     assert float((v_got.cpu() - v_ref)[same].abs().max()) <= 2e-5
+
+
+@pytest.mark.parametrize("T,B", [(8, 4), (16, 3), (8, 40)])
+def test_tc_multi_pass_layers_carry_the_membrane_state_across_calls(T, B):
+    """T = 8 / 16 run as passes of 4 timesteps (small batches: T-parallel passes + a separate LIF kernel).  Two
+    consecutive calls with a caller-owned state must continue the recurrence exactly like the oracle does."""
+    H, cin, cout = 7, 64, 128
+    seq, p = make_block(cin, cout, seed=31)
+    lyr = tc_layer(seq, T, B, H, _lib.OUT_LIF, 2)
+    v = lyr.alloc_state()
+    out, osum = lyr.alloc_out(), lyr.alloc_sum()
+    v_ref = None
+    for call in range(2):
+        s_in = spikes((T, B, cin, H, H), 0.12, 40 + call)
+        cur = O.conv_bn(s_in, p, "c", "b", padding=1)
+        s_ref, v_ref, h_ref = O.lif_multi_step(cur, v=v_ref, return_h=True)
+        lyr.run(engine.stf_from_nchw(s_in.cuda()), out, out_sum=osum, v=v)
+        got = engine.stf_to_nchw(out, T, B, cout, H, H)
+        assert_spikes_match(got, s_ref, h_ref, f"call {call}")
+        if torch.equal(got.cpu(), s_ref):
+            cnt = engine.stf_to_nchw(osum, 1, B, cout, H, H)[0]
+            assert torch.equal(cnt.cpu(), s_ref.sum(0))
+            v_got = torch.empty((B, cout, H, H), dtype=torch.float32, device="cuda")
+            _lib.check(_lib.lib().sd_state_convert(_lib.ptr(v), _lib.ptr(v_got), B, cout, H, H, 0, _lib.stream_ptr()))
+            assert float((v_got.cpu() - v_ref).abs().max()) <= 2e-5
