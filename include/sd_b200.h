@@ -227,6 +227,16 @@ int sd_bn_train_forward(const float* x, const float* gamma_or_null, const float*
 int sd_bn_backward(const float* x, const float* grad_out, const float* mean, const float* var,
                    const float* gamma_or_null, float* grad_x, float* grad_gamma_or_null, float* grad_beta_or_null,
                    int64_t n_outer, int C, int64_t HW, float eps, void* stream);
+/* The same BatchNorm with statistics shared across GPUs (the optional training exchange step of SURVEY.md 8(e); the
+ * reference would use torch.nn.SyncBatchNorm).  The caller all-gathers (count, mean, M2) and all-reduces the two backward
+ * sums over NCCL between these calls (activation_based/layer.py:_SyncBNFn); the normalisation itself is
+ * sd_channel_affine with scale = gamma * invstd, shift = beta - mean * scale. */
+int sd_bn_local_stats(const float* x, float* mean_out, float* m2_out, int64_t n_outer, int C, int64_t HW, void* stream);
+int sd_bn_backward_reduce(const float* x, const float* grad_out, const float* mean, const float* var, float* sum_gy,
+                          float* sum_gy_xhat, int64_t n_outer, int C, int64_t HW, float eps, void* stream);
+int sd_bn_backward_apply(const float* x, const float* grad_out, const float* mean, const float* var, const float* gamma,
+                         const float* mean_gy, const float* mean_gy_xhat, float* grad_x, int64_t n_outer, int C, int64_t HW,
+                         float eps, void* stream);
 
 /* ---- (a12) absorbing-diffusion sampling step ----------------------------------------------------
  * Torch-compatible Philox4x32-10 streams (TORCH/include/ATen/native/cuda/DistributionTemplates.h:50-87):

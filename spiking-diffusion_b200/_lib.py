@@ -26,7 +26,7 @@ SYMBOLS = [
     "sd_stf_from_nchw", "sd_stf_to_nchw", "sd_stf_upsample2x", "sd_stf_subsample2x", "sd_channel_affine", "sd_state_convert", "sd_lif_forward", "sd_lif_backward", "sd_memout", "sd_vq_feature", "sd_vq_lookup",
     "sd_vq_gather", "sd_conv_weight_bytes_simt", "sd_conv_weight_bytes_tc", "sd_conv_workspace_bytes", "sd_conv_weight_layout_tc", "sd_conv_pack_weights_simt",
     "sd_conv_pack_weights_tc", "sd_conv_lif_simt", "sd_conv_lif_tc", "sd_conv_tc_supported", "sd_debug_tc_trace", "sd_conv_wgrad_workspace_bytes", "sd_conv_wgrad",
-    "sd_bn_train_forward", "sd_bn_backward", "sd_philox_uniform",
+    "sd_bn_train_forward", "sd_bn_backward", "sd_bn_local_stats", "sd_bn_backward_reduce", "sd_bn_backward_apply", "sd_philox_uniform",
     "sd_philox_exponential", "sd_philox_offset_increment", "sd_sample_step", "sd_sample_step_dev", "sd_denoiser_input", "sd_to_uint8",
 ]
 
@@ -134,6 +134,9 @@ def _declare(lib: ctypes.CDLL) -> None:
         "sd_conv_wgrad": (i, [pd, vp, vp, vp, vp, vp, vp]),
         "sd_bn_train_forward": (i, [vp, vp, vp, vp, vp, vp, i64, i, i64, f, vp]),
         "sd_bn_backward": (i, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i, i64, f, vp]),
+        "sd_bn_local_stats": (i, [vp, vp, vp, i64, i, i64, vp]),
+        "sd_bn_backward_reduce": (i, [vp, vp, vp, vp, vp, vp, i64, i, i64, f, vp]),
+        "sd_bn_backward_apply": (i, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i, i64, f, vp]),
         "sd_philox_uniform": (i, [vp, i64, u64, u64, i64, i64, ctypes.POINTER(u64), vp]),
         "sd_philox_exponential": (i, [vp, i64, u64, u64, i64, i64, ctypes.POINTER(u64), vp]),
         "sd_philox_offset_increment": (i, [i64, ctypes.POINTER(u64)]),

@@ -53,3 +53,17 @@ def seq_to_ann_forward(x_seq, stateless_module):
         y = stateless_module(y)
     y_shape.extend(y.shape[1:])
     return y.view(y_shape)
+
+
+def convert_sync_batchnorm(net, process_group=None):
+    """Make every train-mode ``layer.BatchNorm2d`` of ``net`` compute its batch statistics over all ranks of
+    ``process_group`` (default: the world group) - the counterpart of ``torch.nn.SyncBatchNorm.convert_sync_batchnorm``
+    for data-parallel training of these models (optional training path).  Eval mode is
+    unaffected (running statistics).  Returns ``net``."""
+    import torch.distributed as dist
+    from . import layer
+    group = process_group if process_group is not None else (dist.group.WORLD if dist.is_initialized() else None)
+    for m in net.modules():
+        if isinstance(m, layer.BatchNorm2d):
+            m.sync_group = group
+    return net

@@ -110,6 +110,62 @@ class _BNFn(torch.autograd.Function):
         return gx, (gg if has_g else None), (gb if has_b else None), None
 
 
+class _SyncBNFn(torch.autograd.Function):
+    """Train-mode BatchNorm2d whose batch statistics span every rank of a process group (the reference would wrap its
+    model in torch.nn.SyncBatchNorm; SURVEY.md 8(e): train-mode BN is the one batch-coupled op of the training path).
+    Forward: local (count, mean, M2) per channel -> all_gather over NCCL -> parallel-variance combination -> affine.
+    Backward: local sums of gy and gy * xhat -> all_reduce -> input gradient; the gamma / beta gradients stay local
+    (DistributedDataParallel averages parameter gradients itself, as with torch's SyncBatchNorm)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, group):
+        import torch.distributed as dist
+        x = x.contiguous().float()
+        n_outer, C = x.shape[0], x.shape[1]
+        hw = x.shape[2] * x.shape[3]
+        stats = torch.empty((3, C), dtype=torch.float32, device=x.device)
+        check(lib().sd_bn_local_stats(ptr(x), ptr(stats[0]), ptr(stats[1]), n_outer, C, hw, stream_ptr()))
+        stats[2].fill_(float(n_outer * hw))
+        world = dist.get_world_size(group)
+        gathered = torch.empty((world, 3, C), dtype=torch.float32, device=x.device)
+        dist.all_gather_into_tensor(gathered, stats, group=group)
+        cnt = gathered[:, 2]                                   # [world, C]
+        total = cnt.sum(0)
+        mean = (gathered[:, 0] * cnt).sum(0) / total
+        m2 = gathered[:, 1].sum(0) + (cnt * (gathered[:, 0] - mean) ** 2).sum(0)
+        var = m2 / total                                       # biased, like F.batch_norm uses for normalisation
+        invstd = torch.rsqrt(var + eps)
+        scale = (gamma if gamma is not None else torch.ones_like(mean)) * invstd
+        shift = (beta if beta is not None else torch.zeros_like(mean)) - mean * scale
+        y = torch.empty_like(x)
+        check(lib().sd_channel_affine(ptr(x), ptr(scale.contiguous()), ptr(shift.contiguous()), ptr(y), n_outer, C, hw,
+                                      stream_ptr()))
+        mean, var = mean.contiguous(), var.contiguous()
+        ctx.save_for_backward(x, mean, var, gamma if gamma is not None else torch.empty(0, device=x.device), total)
+        ctx.meta = (float(eps), gamma is not None, beta is not None, group)
+        ctx.mark_non_differentiable(mean, var, total)
+        return y, mean, var, total
+
+    @staticmethod
+    def backward(ctx, gy, _gm, _gv, _gt):
+        import torch.distributed as dist
+        x, mean, var, gamma, total = ctx.saved_tensors
+        eps, has_g, has_b, group = ctx.meta
+        gy = gy.contiguous().float()
+        n_outer, C = x.shape[0], x.shape[1]
+        hw = x.shape[2] * x.shape[3]
+        sums = torch.empty((2, C), dtype=torch.float32, device=x.device)
+        check(lib().sd_bn_backward_reduce(ptr(x), ptr(gy), ptr(mean), ptr(var), ptr(sums[0]), ptr(sums[1]), n_outer, C, hw,
+                                          eps, stream_ptr()))
+        local = sums.clone()
+        dist.all_reduce(sums, group=group)
+        means = (sums / total).contiguous()
+        gx = torch.empty_like(x)
+        check(lib().sd_bn_backward_apply(ptr(x), ptr(gy), ptr(mean), ptr(var), ptr(gamma) if has_g else None, ptr(means[0]),
+                                         ptr(means[1]), ptr(gx), n_outer, C, hw, eps, stream_ptr()))
+        return gx, (local[1] if has_g else None), (local[0] if has_b else None), None, None
+
+
 class _ConvMixin(base.StepModule):
     def _plan(self, T, B, H, W) -> engine.FusedLayer:
         key = (T, B, H, W, self.weight.data_ptr(), self.weight._version,
@@ -186,14 +242,20 @@ class BatchNorm2d(nn.BatchNorm2d, base.StepModule):
         if self.training or not self.track_running_stats:
             # batch statistics over T*N*H*W (functional.seq_to_ann_forward flattens T into the batch, layer.py:458-465)
             x4 = x.flatten(0, 1) if x.dim() == 5 else x
-            y, mean, var = _BNFn.apply(x4, self.weight, self.bias, self.eps)
+            group = getattr(self, "sync_group", None)
+            if group is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
+                y, mean, var, total = _SyncBNFn.apply(x4, self.weight, self.bias, self.eps, group)
+                unbias = total / (total - 1).clamp(min=1)     # global element count per channel, kept on the device
+            else:
+                y, mean, var = _BNFn.apply(x4, self.weight, self.bias, self.eps)
+                n = x4.numel() // x4.shape[1]
+                unbias = n / max(n - 1, 1)
             if self.track_running_stats:
                 with torch.no_grad():   # F.batch_norm's running update: momentum, unbiased variance
-                    n = x4.numel() // x4.shape[1]
                     self.num_batches_tracked += 1
                     mom = self.momentum if self.momentum is not None else 1.0 / float(self.num_batches_tracked)
                     self.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
-                    self.running_var.mul_(1 - mom).add_(var * (n / max(n - 1, 1)), alpha=mom)
+                    self.running_var.mul_(1 - mom).add_(var * unbias, alpha=mom)
             return y.view(x.shape)
         scale, shift = engine.fold_bn(None, self.num_features, self, x.device)
         xc = x.contiguous().float()

@@ -237,7 +237,72 @@ __global__ void __launch_bounds__(256) bn_backward_kernel(const float* __restric
   }
 }
 
+// ---- pieces of train-mode BatchNorm for statistics shared across GPUs (SyncBN) ------------------------------------
+// local mean and centred sum of squares M2 per channel; the caller combines the ranks' (count, mean, M2) triples with the
+// parallel-variance formula, which keeps the two-pass accuracy of the single-GPU kernel
+__global__ void __launch_bounds__(256) bn_local_stats_kernel(const float* __restrict__ x, float* __restrict__ mean_out,
+                                                             float* __restrict__ m2_out, int64_t n_outer, int C,
+                                                             int64_t HW) {
+  __shared__ float sm[16];
+  const int c = blockIdx.x;
+  const int64_t cnt = n_outer * HW;
+  float v[1] = {0.f};
+  for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int64_t n = i / HW, p = i - n * HW;
+    v[0] += x[(n * C + c) * HW + p];
+  }
+  block_reduce<1>(v, sm);
+  const float mean = v[0] / (float)cnt;
+  float q[1] = {0.f};
+  for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int64_t n = i / HW, p = i - n * HW;
+    const float dlt = x[(n * C + c) * HW + p] - mean;
+    q[0] = fmaf(dlt, dlt, q[0]);
+  }
+  block_reduce<1>(q, sm);
+  if (threadIdx.x == 0) { mean_out[c] = mean; m2_out[c] = q[0]; }
+}
+
+// local sums of gy and gy * xhat per channel (xhat from the GLOBAL mean / variance)
+__global__ void __launch_bounds__(256) bn_backward_reduce_kernel(const float* __restrict__ x, const float* __restrict__ gy,
+                                                                 const float* __restrict__ mean, const float* __restrict__ var,
+                                                                 float* __restrict__ sum_gy, float* __restrict__ sum_gy_xhat,
+                                                                 int64_t n_outer, int C, int64_t HW, float eps) {
+  __shared__ float sm[16];
+  const int c = blockIdx.x;
+  const int64_t cnt = n_outer * HW;
+  const float mu = mean[c], invstd = rsqrtf(var[c] + eps);
+  float v[2] = {0.f, 0.f};
+  for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int64_t n = i / HW, p = i - n * HW;
+    const int64_t o = (n * C + c) * HW + p;
+    const float g = gy[o];
+    v[0] += g;
+    v[1] = fmaf(g, (x[o] - mu) * invstd, v[1]);
+  }
+  block_reduce<2>(v, sm);
+  if (threadIdx.x == 0) { sum_gy[c] = v[0]; sum_gy_xhat[c] = v[1]; }
+}
+
+// gx = gamma * invstd * (gy - mean_gy - xhat * mean_gy_xhat) with the GLOBAL means of gy and gy * xhat
+__global__ void __launch_bounds__(256) bn_backward_apply_kernel(const float* __restrict__ x, const float* __restrict__ gy,
+                                                                const float* __restrict__ mean, const float* __restrict__ var,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ mean_gy,
+                                                                const float* __restrict__ mean_gy_xhat, float* __restrict__ gx,
+                                                                int64_t n_outer, int C, int64_t HW, float eps) {
+  const int64_t total = n_outer * C * HW;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)((o / HW) % C);
+    const float invstd = rsqrtf(var[c] + eps);
+    const float xhat = (x[o] - mean[c]) * invstd;
+    const float gm = gamma ? gamma[c] : 1.f;
+    gx[o] = gm * invstd * (gy[o] - mean_gy[c] - xhat * mean_gy_xhat[c]);
+  }
+}
+
 }  // namespace sd
+
 
 using namespace sd;
 
@@ -309,6 +374,41 @@ int sd_bn_backward(const float* x, const float* grad_out, const float* mean, con
   SD_DEVICE_OR_RETURN();
   bn_backward_kernel<<<(unsigned)C, 256, 0, as_stream(stream)>>>(x, grad_out, mean, var, gamma, grad_x, grad_gamma, grad_beta,
                                                                 n_outer, C, HW, eps);
+  SD_LAUNCH_CHECK();
+  return SD_OK;
+}
+
+int sd_bn_local_stats(const float* x, float* mean_out, float* m2_out, int64_t n_outer, int C, int64_t HW, void* stream) {
+  SD_REQUIRE(n_outer >= 1 && C >= 1 && HW >= 1, "bn_local_stats: bad shape");
+  SD_REQUIRE(x && mean_out && m2_out, "null pointer argument");
+  SD_DEVICE_OR_RETURN();
+  bn_local_stats_kernel<<<(unsigned)C, 256, 0, as_stream(stream)>>>(x, mean_out, m2_out, n_outer, C, HW);
+  SD_LAUNCH_CHECK();
+  return SD_OK;
+}
+
+int sd_bn_backward_reduce(const float* x, const float* grad_out, const float* mean, const float* var, float* sum_gy,
+                          float* sum_gy_xhat, int64_t n_outer, int C, int64_t HW, float eps, void* stream) {
+  SD_REQUIRE(n_outer >= 1 && C >= 1 && HW >= 1, "bn_backward_reduce: bad shape");
+  SD_REQUIRE(x && grad_out && mean && var && sum_gy && sum_gy_xhat, "null pointer argument");
+  SD_DEVICE_OR_RETURN();
+  bn_backward_reduce_kernel<<<(unsigned)C, 256, 0, as_stream(stream)>>>(x, grad_out, mean, var, sum_gy, sum_gy_xhat, n_outer,
+                                                                       C, HW, eps);
+  SD_LAUNCH_CHECK();
+  return SD_OK;
+}
+
+int sd_bn_backward_apply(const float* x, const float* grad_out, const float* mean, const float* var, const float* gamma,
+                         const float* mean_gy, const float* mean_gy_xhat, float* grad_x, int64_t n_outer, int C, int64_t HW,
+                         float eps, void* stream) {
+  SD_REQUIRE(n_outer >= 1 && C >= 1 && HW >= 1, "bn_backward_apply: bad shape");
+  SD_REQUIRE(x && grad_out && mean && var && mean_gy && mean_gy_xhat && grad_x, "null pointer argument");
+  SD_DEVICE_OR_RETURN();
+  const int64_t total = n_outer * C * HW;
+  int64_t bl = (total + 255) / 256;
+  if (bl > 148 * 16) bl = 148 * 16;
+  bn_backward_apply_kernel<<<(unsigned)bl, 256, 0, as_stream(stream)>>>(x, grad_out, mean, var, gamma, mean_gy, mean_gy_xhat,
+                                                                        grad_x, n_outer, C, HW, eps);
   SD_LAUNCH_CHECK();
   return SD_OK;
 }
