@@ -61,6 +61,30 @@ def main():
     for n, p in ref.named_parameters():
         if n != "0.bias":   # a conv bias in front of a train-mode BN has no effect: its gradient is rounding noise
             errs["grad " + n] = rel(grads[n], p.grad)
+    # DistributedDataParallel over the spiking denoiser in training mode (custom autograd functions, SyncBN inside):
+    # one optimiser step; the averaged gradients must be finite and identical on every rank
+    from spiking_diffusion_b200 import synth
+    from spiking_diffusion_b200.snn_model.vq_diffusion import DummyModel
+    den = DummyModel(1, 32, T=2)
+    functional.set_step_mode(den, "m")
+    den.load_state_dict(synth.synth_denoiser_state(0, n_channel=1, num_embeddings=32, num_timesteps=49))
+    den = functional.convert_sync_batchnorm(den.cuda().train())
+    ddp = torch.nn.parallel.DistributedDataParallel(den, device_ids=[int(os.environ["LOCAL_RANK"])])
+    opt = torch.optim.AdamW(ddp.parameters(), lr=1e-3)
+    gd = torch.Generator().manual_seed(100 + rank)
+    xd = torch.randint(0, 33, (4, 1, 7, 7), generator=gd).float().cuda()
+    td = torch.randint(1, 50, (4,), generator=gd).cuda()
+    tgt = torch.randint(0, 32, (4, 7, 7), generator=gd).cuda()
+    before = [p.detach().clone() for p in ddp.parameters()]
+    loss = torch.nn.functional.cross_entropy(ddp(xd, td), tgt)
+    opt.zero_grad(); loss.backward()
+    flat = torch.cat([p.grad.flatten() for p in ddp.parameters()])
+    other = flat.clone()
+    dist.broadcast(other, src=0)
+    errs["ddp grads differ across ranks"] = float((flat - other).abs().max())
+    errs["ddp grads not finite"] = 0.0 if bool(torch.isfinite(flat).all()) and float(flat.abs().max()) > 0 else 1.0
+    opt.step(); functional.reset_net(den)
+    errs["ddp step left parameters unchanged"] = 0.0 if any(not torch.equal(a, b) for a, b in zip(before, ddp.parameters())) else 1.0
     bad = {k: v for k, v in errs.items() if not v <= 2e-5}
     t = torch.tensor([len(bad)], device="cuda")
     dist.all_reduce(t)
