@@ -70,7 +70,7 @@ struct TcConfig {
   int halo, rows_ld;
   int ndx;         // 1: one copy of the rows, taps shift by dy*Wp+dx rows (16-byte aligned starts);
                    // 3: three copies pre-shifted by dx = -1,0,+1 so that every tap start is 128-byte aligned
-                   //    (needs Wp % 8 == 0): shared-memory operand fetch of a misaligned core matrix costs 2x
+                   //    (needs Wp % 8 == 0).  Measured: no gain, the cost of an MMA does not depend on the alignment
   uint32_t a_stage_bytes, b_stage_bytes, smem_bytes;
   int n_tiles, m_tiles, num_kblocks, c0_blocks;
 };
@@ -463,6 +463,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
                   const uint64_t adesc = ((uint64_t)desc_hi << 32) | (a_lo + ks * a_step_k);
                   const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (b_lo0 + sp * b_step_sp + ks * b_step_k);
                   if (PAIR) tc_mma_f16_masked_pair(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first, km);
+                  else if (p.dbg & 4) tc_mma_f16(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first);   // timing experiment
                   else tc_mma_f16_masked(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first, km[0], km[1], km[2], km[3]);
                 }
               }
@@ -763,7 +764,8 @@ __global__ void __launch_bounds__(256) lif_from_currents_kernel(const TcParams p
 //   SD_TC_N256, SD_TC_WIDE256       N = 256 tiles with 2 timesteps per pass
 //   SD_TC_NTILE, SD_TC_KBLK, SD_TC_ACC_STAGES, SD_TC_ALIGN   tile shape overrides
 //   SD_TC_PERSIST=0         one work unit per CTA / cluster
-//   SD_TC_DBG (with sd_debug_tc_trace)   1: skip spike stores, 2: skip TMEM loads (timing experiments only)
+//   SD_TC_DBG (with sd_debug_tc_trace)   1: skip spike stores, 2: skip TMEM loads, 4: un-masked MMAs in the single-CTA
+//                           kernel (timing experiments only; 4 gives wrong results at image borders)
 static int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return s ? atoi(s) : dflt;
@@ -819,7 +821,7 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
     const int m_tiles = (int)((rows + kTileRows - 1) / kTileRows);
     const int conc = d->concurrent > 1 ? d->concurrent : 1;   // sub-batches on other streams fill the SMs instead
     // Only when the tiles cannot be paired (a single M tile): the cycle-stamp trace shows that an un-paired MMA costs
-    // 72-79 cycles whatever N is (the fetch of the row-shifted A rows dominates) while a paired N = 128 MMA does 8x the
+    // 72-79 cycles whatever N is (reading the 4 KB A operand from shared memory bounds it) while a paired N = 128 MMA does 8x the
     // work of an N = 32 one in 64 cycles, and the K loop per CTA - the critical path of a small batch - is the same.
     const bool can_pair = env_int("SD_TC_PAIR", 1) && m_tiles >= 2 && n_tile == 128;
     while (n_tile > 32 && env_int("SD_TC_SMALL_BATCH_SPLIT", 1) && !can_pair &&
