@@ -28,6 +28,17 @@ class StepModule:
         self._step_mode = value
 
 
+class LazyState:
+    """A memory value that is produced on first access (the fused whole-model plans keep LIF states in their planar
+    kernel layout; the reference-layout tensor is only built if somebody reads ``node.v`` before the next reset)."""
+
+    def __init__(self, fn):
+        self._fn = fn
+
+    def materialize(self):
+        return self._fn()
+
+
 class MemoryModule(nn.Module, StepModule):
     def __init__(self):
         super().__init__()
@@ -84,7 +95,10 @@ class MemoryModule(nn.Module, StepModule):
         if "_memories" in self.__dict__:
             memories = self.__dict__["_memories"]
             if name in memories:
-                return memories[name]
+                value = memories[name]
+                if isinstance(value, LazyState):
+                    value = memories[name] = value.materialize()
+                return value
         return super().__getattr__(name)
 
     def __setattr__(self, name: str, value) -> None:
@@ -101,11 +115,23 @@ class MemoryModule(nn.Module, StepModule):
         else:
             super().__delattr__(name)
 
+    def _resolve_lazy(self):
+        for key, value in self._memories.items():
+            if isinstance(value, LazyState):
+                self._memories[key] = value.materialize()
+
+    def memory_is_reset(self, name: str) -> bool:
+        """True if the memory still holds its (non-tensor) reset value; does not materialise a lazy state."""
+        value = self._memories[name]
+        return not isinstance(value, (torch.Tensor, LazyState))
+
     def memories(self):
+        self._resolve_lazy()
         for value in self._memories.values():
             yield value
 
     def named_memories(self):
+        self._resolve_lazy()
         for name, value in self._memories.items():
             yield name, value
 
@@ -115,12 +141,14 @@ class MemoryModule(nn.Module, StepModule):
                 value.detach_()
 
     def _apply(self, fn, *args, **kwargs):
+        self._resolve_lazy()
         for key, value in self._memories.items():
             if isinstance(value, torch.Tensor):
                 self._memories[key] = fn(value)
         return super()._apply(fn, *args, **kwargs)
 
     def _replicate_for_data_parallel(self):
+        self._resolve_lazy()
         replica = super()._replicate_for_data_parallel()
         replica._memories = self._memories.copy()
         return replica

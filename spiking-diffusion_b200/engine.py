@@ -506,21 +506,29 @@ class VQVAEPlan:
         self.sg, self.sd1, self.sd2 = self.gen.alloc_out(), self.d1.alloc_out(), self.d2.alloc_out()
         self.recon = self.d3.alloc_out()
         self._vq = vq
+        self._states, self._captured = None, None
         self._coef_vq = (ctypes.c_float * T)(*vq.memout.coef.detach().reshape(-1).cpu().tolist()[:T])
+
+    def _state(self, name: str, lyr: "FusedLayer") -> Optional[torch.Tensor]:
+        """Fresh LIF state buffer (planar layout, reset value) for layer ``name`` while states are being captured."""
+        if self._states is None:
+            return None
+        self._states[name] = (lyr.alloc_state(), lyr)
+        return self._states[name][0]
 
     def encode(self, x: torch.Tensor, const_over_T: bool = False) -> torch.Tensor:
         """x: fp32 [T,B,C,H,W] (or [B,C,H,W] with const_over_T=True: the frame repeated T times, R/main.py:133)."""
         if const_over_T:
-            self.e1c.run(x.contiguous(), self.s1)
+            self.e1c.run(x.contiguous(), self.s1, v=self._state("e1", self.e1c))
         else:
-            self.e1.run(x.contiguous(), self.s1)
+            self.e1.run(x.contiguous(), self.s1, v=self._state("e1", self.e1))
         if self.tc_encoder:
-            self.e2.run(self.s1, self.s2_full)
+            self.e2.run(self.s1, self.s2_full, v=self._state("e2", self.e2))
             check(lib().sd_stf_subsample2x(ptr(self.s2_full), ptr(self.s2), self.T, self.B, self.e2.C_out,
                                            self.e1.H_out, self.e1.W_out, stream_ptr()))
         else:
-            self.e2.run(self.s1, self.s2)
-        self.e3.run(self.s2, self.s3)
+            self.e2.run(self.s1, self.s2, v=self._state("e2", self.e2))
+        self.e3.run(self.s2, self.s3, v=self._state("e3", self.e3))
         return self.s3
 
     def quantize_indices(self, spikes_stf: torch.Tensor) -> torch.Tensor:
@@ -536,20 +544,20 @@ class VQVAEPlan:
         L, vq = lib(), self._vq
         check(L.sd_vq_gather(ptr(idx), ptr(vq.embeddings.weight.detach()), ptr(self.q), self.B, self.D, self.h, self.w,
                              self.K, stream_ptr()))
-        self.gen.run(self.q, self.sg)
+        self.gen.run(self.q, self.sg, v=self._state("gen", self.gen))
         return self.sg
 
     def decode(self, e_stf: torch.Tensor) -> torch.Tensor:
         if self.tc_decoder:
             L, d1, d2 = lib(), self.d1.desc, self.d2.desc
             check(L.sd_stf_upsample2x(ptr(e_stf), ptr(self.up0), self.T, self.B, d1.C_in, self.h, self.w, stream_ptr()))
-            self.d1.run(self.up0, self.sd1)
+            self.d1.run(self.up0, self.sd1, v=self._state("d1", self.d1))
             check(L.sd_stf_upsample2x(ptr(self.sd1), ptr(self.up1), self.T, self.B, d2.C_in, 2 * self.h, 2 * self.w,
                                       stream_ptr()))
-            self.d2.run(self.up1, self.sd2)
+            self.d2.run(self.up1, self.sd2, v=self._state("d2", self.d2))
         else:
-            self.d1.run(e_stf, self.sd1)
-            self.d2.run(self.sd1, self.sd2)
+            self.d1.run(e_stf, self.sd1, v=self._state("d1", self.d1))
+            self.d2.run(self.sd1, self.sd2, v=self._state("d2", self.d2))
         self.d3.run(self.sd2, self.recon)
         return self.recon
 
@@ -557,12 +565,37 @@ class VQVAEPlan:
         """R/main.py:388-399: sampled indices -> tanh(memout(decoder(poisson(quantize(idx)))))."""
         return self.decode(self.generate(idx.reshape(-1)))
 
-    def forward(self, x: torch.Tensor, const_over_T: bool = False):
-        z = self.encode(x, const_over_T)
-        idx = self.quantize_indices(z)
-        e = self.generate(idx)
-        rec = self.decode(e)
+    def forward(self, x: torch.Tensor, const_over_T: bool = False, capture_states: bool = False):
+        """Returns (generator spikes STF, reconstruction, code indices).  With ``capture_states`` the final membrane
+        potential of every LIF layer is kept (``self.states()``) so that a caller following the reference's state
+        protocol can hand it to the modules; otherwise the states are consumed inside the kernels."""
+        self._states = {} if capture_states else None
+        try:
+            z = self.encode(x, const_over_T)
+            idx = self.quantize_indices(z)
+            e = self.generate(idx)
+            rec = self.decode(e)
+        finally:
+            captured, self._states = self._states, None
+        self._captured = captured
         return e, rec, idx
+
+    def states(self):
+        """{layer name: zero-argument function returning the final LIF state as fp32 [B, C, H, W]} of the last
+        ``forward(capture_states=True)``.  The conversion from the planar kernel layout runs when the function is
+        called; the tensor-core encoder route computes enc.conv2 at stride 1, so its state is the even positions."""
+        out = {}
+        for name, (buf, lyr) in (self._captured or {}).items():
+            d = lyr.desc
+
+            def make(buf=buf, d=d, sub=(name == "e2" and self.tc_encoder)):
+                def fn():
+                    v = torch.empty((d.B, d.C_out, d.H_out, d.W_out), dtype=torch.float32, device=buf.device)
+                    check(lib().sd_state_convert(ptr(buf), ptr(v), d.B, d.C_out, d.H_out, d.W_out, 0, stream_ptr()))
+                    return v[..., ::2, ::2].contiguous() if sub else v
+                return fn
+            out[name] = make()
+        return out
 
     def flops(self) -> int:
         return sum(l.flops() for l in (self.e1, self.e2, self.e3, self.gen, self.d1, self.d2, self.d3))

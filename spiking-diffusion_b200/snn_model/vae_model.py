@@ -18,7 +18,7 @@ import torch.nn.functional as F
 
 from .. import _lib, engine
 from .._lib import check, lib, ptr, stream_ptr
-from ..activation_based import layer, neuron, surrogate
+from ..activation_based import base, layer, neuron, surrogate
 from .snn_layers import PSP, MembraneOutputLayer
 
 
@@ -200,6 +200,8 @@ class SNN_VQVAE(nn.Module):
     def forward(self, x, image):
         """x: [T, B, C, H, W].  eval -> (e, x_recon, encoding_indices)   (vae_model.py:181-187);
         train -> (e_q_loss, recon_loss, real_recon_loss)                   (vae_model.py:189-196)."""
+        if not self.training and isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 5 and self._all_lif_reset():
+            return self._forward_fused(x)
         z = self.encoder(x)
         if not self.training:
             e, enco = self.vq_layer(z)
@@ -212,6 +214,28 @@ class SNN_VQVAE(nn.Module):
         real_recon_loss = F.mse_loss(x_recon, image)
         recon_loss = real_recon_loss / self.data_variance
         return e_q_loss, recon_loss, real_recon_loss
+
+    def _lif_nodes(self):
+        """(plan layer name, LIF module) of every spiking layer of the eval forward, in execution order."""
+        enc, gen, dec = self.encoder.snn_convs, self.vq_layer.poisson, self.decoder.snn_convs
+        return (("e1", enc[2]), ("e2", enc[5]), ("e3", enc[8]), ("gen", gen[2]), ("d1", dec[2]), ("d2", dec[5]))
+
+    def _all_lif_reset(self) -> bool:
+        return all(isinstance(n, neuron.LIFNode) and n.memory_is_reset("v") for _, n in self._lif_nodes())
+
+    @torch.no_grad()
+    def _forward_fused(self, x):
+        """Eval forward from freshly reset states as ONE fused chain (engine.VQVAEPlan) instead of module by module.
+        The reference's state protocol is kept: every LIFNode.v holds the final membrane potential afterwards (built
+        from the kernels' planar layout only if it is read before the next reset)."""
+        T, B, _, H, W = x.shape
+        plan = self.plan(T, B, H, W)
+        e_stf, rec, idx = plan.forward(x.float(), capture_states=True)
+        states = plan.states()
+        for name, node in self._lif_nodes():
+            node.v = base.LazyState(states[name])
+        e = engine.stf_to_nchw(e_stf, T, B, self.embedding_dim, plan.h, plan.w)
+        return e, rec.clone(), idx.clone()
 
     @torch.no_grad()
     def decode_indices(self, sample: torch.Tensor, T: int = None) -> torch.Tensor:

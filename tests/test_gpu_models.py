@@ -207,3 +207,37 @@ def test_load_reference_checkpoint_into_other_T():
         m.load_state_dict(ckpt)
     load_reference_state_dict(m, ckpt)
     assert m.memout.coef.shape == (4, 1, 1, 1, 1) and torch.equal(m.encoder.snn_convs[0].weight, ckpt["encoder.snn_convs.0.weight"])
+
+
+def test_fused_eval_forward_keeps_the_lif_state_protocol():
+    """SNN_VQVAE.forward from reset states runs as one fused chain; every LIFNode.v must afterwards hold what the
+    module-by-module path leaves there (built lazily), and a second call without reset must continue from it."""
+    T, B, K = 4, 6, 128
+    m, sd = make_vqvae(T, K, seed=3)
+    img = synth.synth_images(3, B).cuda()
+    xs = img.unsqueeze(0).repeat(T, 1, 1, 1, 1)
+    nodes = [n for _, n in m._lif_nodes()]
+    # module by module (the reference's own call sequence)
+    functional.reset_net(m)
+    z = m.encoder(xs)
+    e_ref, idx_ref = m.vq_layer(z)
+    rec_ref = m.memout(m.decoder(e_ref), apply_tanh=True)
+    v_ref = [n.v.clone() for n in nodes]
+    z2 = m.encoder(xs)                       # second pass without reset: the states carry over
+    e_ref2, idx_ref2 = m.vq_layer(z2)
+    # fused
+    functional.reset_net(m)
+    assert m._all_lif_reset()
+    e, rec, idx = m(xs, img)
+    assert not m._all_lif_reset()
+    assert torch.equal(idx, idx_ref) and torch.equal(e, e_ref)
+    assert float((rec - rec_ref).abs().mean()) <= IMAGE_TOL
+    for n, vr in zip(nodes[:4], v_ref[:4]):  # encoder + generator states: same kernels' arithmetic order up to the tc route
+        assert n.v.shape == vr.shape
+        assert float((n.v - vr).abs().max()) <= 1e-4 or float(((n.v - vr).abs() > 1e-4).float().mean()) <= 1e-3
+    for n, vr in zip(nodes[4:], v_ref[4:]):
+        assert n.v.shape == vr.shape
+    e2, rec2, idx2 = m(xs, img)              # not reset: continues from the (materialised) states, module by module
+    assert float((idx2 != idx_ref2).float().mean()) <= 0.02
+    functional.reset_net(m)
+    assert m._all_lif_reset()
