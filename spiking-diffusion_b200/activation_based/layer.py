@@ -345,7 +345,7 @@ class SpikingSequential(nn.Sequential):
             if lif is not None:
                 d = plan.desc
                 v_planar = plan.alloc_state()
-                if isinstance(lif.v, torch.Tensor):  # continue from the stored state (neuron.py:972-1010)
+                if not lif.memory_is_reset("v") and isinstance(lif.v, torch.Tensor):  # continue from the stored state (neuron.py:972-1010)
                     check(lib().sd_state_convert(ptr(lif.v.contiguous().float()), ptr(v_planar), d.B, d.C_out, d.H_out,
                                                  d.W_out, 1, stream_ptr()))
             out = buf if plan.desc.out_kind == _lib.OUT_LIF else plan.alloc_out()
@@ -356,10 +356,13 @@ class SpikingSequential(nn.Sequential):
                 cur = plan.upsample_buf
             plan.run(cur, out, v=v_planar)
             if lif is not None:
-                d = plan.desc
-                v_new = torch.empty((d.B, d.C_out, d.H_out, d.W_out), dtype=torch.float32, device=x.device)
-                check(lib().sd_state_convert(ptr(v_planar), ptr(v_new), d.B, d.C_out, d.H_out, d.W_out, 0, stream_ptr()))
-                lif.v = v_new
+                # the final membrane potential stays in the kernels' planar layout; LIFNode.v is built from it only if
+                # it is read before the next reset (functional.reset_net follows every forward in the reference)
+                def to_reference_layout(buf=v_planar, d=plan.desc):
+                    v_new = torch.empty((d.B, d.C_out, d.H_out, d.W_out), dtype=torch.float32, device=buf.device)
+                    check(lib().sd_state_convert(ptr(buf), ptr(v_new), d.B, d.C_out, d.H_out, d.W_out, 0, stream_ptr()))
+                    return v_new
+                lif.v = base.LazyState(to_reference_layout)
             cur = out
         last = self._plans[-1].desc
         if last.out_kind == _lib.OUT_LIF:
