@@ -120,6 +120,11 @@ class MemoryModule(nn.Module, StepModule):
             if isinstance(value, LazyState):
                 self._memories[key] = value.materialize()
 
+    def __getstate__(self):
+        # pickling / torch.save(module): closures of lazy states do not pickle, tensors do
+        self._resolve_lazy()
+        return self.__dict__
+
     def memory_is_reset(self, name: str) -> bool:
         """True if the memory still holds its (non-tensor) reset value; does not materialise a lazy state."""
         value = self._memories[name]

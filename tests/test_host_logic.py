@@ -193,3 +193,31 @@ def test_strided_layers_restated_for_the_tensor_core_kernel_are_identities():
     assert not engine._UpsampledConvT.eligible(torch.nn.ConvTranspose2d(16, 32, 3, stride=1, padding=1))
     assert not engine._UpsampledConvT.eligible(torch.nn.ConvTranspose2d(16, 3, 3, stride=2, padding=1, output_padding=1))
     assert not engine._Stride1Conv.eligible(torch.nn.Conv2d(1, 32, 3, stride=2, padding=1))
+
+
+def test_lazy_memory_states_follow_the_memory_protocol():
+    import copy
+    import pickle
+    n = neuron.LIFNode()
+    assert n.memory_is_reset("v")
+    calls = []
+
+    def build():
+        calls.append(1)
+        return torch.arange(6.0).reshape(2, 3)
+
+    n.v = base.LazyState(build)
+    assert not n.memory_is_reset("v") and calls == []          # nothing is built until somebody looks
+    assert torch.equal(n.v, torch.arange(6.0).reshape(2, 3)) and calls == [1]
+    assert torch.equal(n.v, n.v) and calls == [1]               # built once, then a plain tensor
+    n.v = base.LazyState(build)
+    n.reset()
+    assert n.memory_is_reset("v") and n.v == 0.0 and calls == [1]   # reset discards it without building
+    n.v = base.LazyState(build)
+    m = pickle.loads(pickle.dumps(n))                           # pickling materialises
+    assert torch.equal(m.v, torch.arange(6.0).reshape(2, 3))
+    n.v = base.LazyState(build)
+    c = copy.deepcopy(n)
+    assert torch.equal(c.v, torch.arange(6.0).reshape(2, 3))
+    n.v = base.LazyState(build)
+    assert [tuple(v.shape) for v in n.memories()] == [(2, 3)]
