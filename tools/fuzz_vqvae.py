@@ -1,0 +1,57 @@
+"""Random-shape check of the fused VQ-VAE plan (tensor-core encoder / decoder routes included) and of the module
+forward against the CPU oracle (GPU box).  Usage: python tools/fuzz_vqvae.py [n_cases] [seed]"""
+import os
+import random
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import snn_oracle as O  # noqa: E402  (checker)
+from spiking_diffusion_b200 import engine, synth  # noqa: E402
+from spiking_diffusion_b200.activation_based import functional  # noqa: E402
+from spiking_diffusion_b200.snn_model.vae_model import SNN_VQVAE  # noqa: E402
+
+
+def main():
+    n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    bad = 0
+    for case in range(n_cases):
+        T = rng.choice([1, 2, 4, 4, 8, 16])
+        size = rng.choice([8, 12, 16, 20, 24, 28, 28, 32])
+        in_dim = rng.choice([1, 1, 3])
+        K = rng.choice([64, 128, 512])
+        B = rng.choice([1, 2, 3, 5, 9, 17, 33])
+        sd = synth.synth_vqvae_state(case, in_dim=in_dim, num_embeddings=K, T=T)
+        m = SNN_VQVAE(in_dim, 16, K, torch.tensor(1.0), T=T)
+        functional.set_step_mode(m, "m")
+        m.load_state_dict(sd)
+        m = m.eval().cuda()
+        img = synth.synth_images(case, B, in_dim=in_dim, size=size)
+        xs = img.unsqueeze(0).repeat(T, 1, 1, 1, 1)
+        tr = O.Trace()
+        e_ref, rec_ref, idx_ref = O.vqvae_forward_eval(xs, sd, trace=tr)
+        plan = m.plan(T, B, size, size)
+        e, rec, idx = plan.forward(img.cuda(), const_over_T=True)
+        margin = O.vq_margin(tr["feat"].reshape(-1, 16), sd["vq_layer.embeddings.weight"])
+        hard_idx = int(((idx.cpu() != idx_ref) & (margin > 1e-4)).sum())
+        e_got = engine.stf_to_nchw(e, T, B, 16, plan.h, plan.w).cpu()
+        flips = float((e_got != e_ref).float().mean())
+        err = float((rec.cpu() - rec_ref).abs().mean())
+        # the module API (fused from reset states) must agree with the plan
+        e2, rec2, idx2 = m(xs.cuda(), img.cuda())
+        functional.reset_net(m)
+        same = torch.equal(idx2, idx) and float((rec2 - rec).abs().max()) <= 1e-6
+        ok = hard_idx == 0 and flips <= 1e-3 and err <= 1e-3 and same
+        bad += not ok
+        print(f"case {case}: T={T} {in_dim}x{size}x{size} K={K} B={B} tc_enc={plan.tc_encoder} tc_dec={plan.tc_decoder}: "
+              f"index mismatches outside margin {hard_idx}, generator flip rate {flips:.1e}, image mean-abs err {err:.1e}, "
+              f"module==plan {same}", "" if ok else "<-- CHECK", flush=True)
+    print("suspicious cases:", bad)
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
