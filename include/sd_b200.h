@@ -259,7 +259,8 @@ int sd_philox_offset_increment(int64_t numel_global, uint64_t* inc_out);
  *   probs = Categorical(logits = logits / temp).probs                           (:134-137)
  *   x0_hat = argmax(probs / Exp(1))                                             (:138, multinomial n=1)
  *   x_t[changes] = x0_hat[changes]                                              (:140)
- * logits: fp32 [n_tokens, K] (channels last); x_t: int64 [n_tokens]; unmasked: uint8 [n_tokens].
+ * logits: fp32 [n_tokens, K] (channels last), 1 <= K <= 1024 (128-bit loads when K is a multiple of 128 and the
+ * pointer is 16-byte aligned); x_t: int64 [n_tokens]; unmasked: uint8 [n_tokens].
  * The shard [token_base, token_base + n_tokens) of a global batch of n_tokens_global tokens draws the
  * Philox values of its GLOBAL element indices, so a batch sharded over GPUs reproduces the single-GPU
  * stream.  offset_uniform / offset_exponential are the generator offsets of the two

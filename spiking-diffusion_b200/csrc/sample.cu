@@ -102,12 +102,14 @@ __global__ void philox_fill_kernel(float* __restrict__ out, int64_t numel, int64
   }
 }
 
-// One warp per token.  K is a multiple of 128; each lane keeps K/32 logits in registers (K <= 1024).
+// One warp per token; each lane keeps ceil(K/32) logits in registers (K <= 1024).
 // Templated on the register-array size so that K = 128 compiles to a compact loop (the 32-wide unroll is ~100 KB of
-// code and thrashes the instruction cache when only 4 of its 32 iterations execute).
+// code and thrashes the instruction cache when only 4 of its 32 iterations execute).  VEC: K is a multiple of 128 and
+// lane l holds elements 128 j + 4 l + e (128-bit loads); otherwise any K, lane l holds elements 32 j + l, and the
+// missing tail elements are -inf (probability 0, never drawn).
 constexpr int kMaxPerLaneAll = 32;
 
-template <int kMaxPerLane>
+template <int kMaxPerLane, bool VEC>
 __global__ void __launch_bounds__(256) sample_step_kernel(const float* __restrict__ logits, int64_t* __restrict__ x_t,
                                                           uint8_t* __restrict__ unmasked, int64_t* __restrict__ x0_hat,
                                                           int64_t n_tokens, int K, float inv_t, float inv_temp,
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(256) sample_step_kernel(const float* __restric
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int per_lane = K >> 5;
+  const int per_lane = VEC ? K >> 5 : (K + 31) >> 5;
   for (int64_t tok = warp_global; tok < n_tokens; tok += n_warps) {
     const int64_t gtok = token_base + tok;
     // ---- where to unmask (vq_diffusion.py:118-124) ----
@@ -133,16 +135,28 @@ __global__ void __launch_bounds__(256) sample_step_kernel(const float* __restric
     // ---- Categorical(logits / temp): normalise by logsumexp, softmax -> probs (categorical.py:78) ----
     // element k of lane: k = lane*4 + 128*j + e  (128-bit loads, consecutive lanes -> consecutive 16 B)
     float l[kMaxPerLane];
-    const float4* row = reinterpret_cast<const float4*>(logits + tok * (int64_t)K);
     float mx = -INFINITY;
+    if (VEC) {
+      const float4* row = reinterpret_cast<const float4*>(logits + tok * (int64_t)K);
 #pragma unroll
-    for (int j = 0; j < kMaxPerLane / 4; ++j) {
-      if (j * 4 < per_lane) {
-        float4 q = row[j * 32 + lane];
-        // torch's CUDA `tensor / python_float` multiplies by the fp32 reciprocal (BinaryDivTrueKernel.cu)
-        l[4 * j + 0] = __fmul_rn(q.x, inv_temp); l[4 * j + 1] = __fmul_rn(q.y, inv_temp);
-        l[4 * j + 2] = __fmul_rn(q.z, inv_temp); l[4 * j + 3] = __fmul_rn(q.w, inv_temp);
-        mx = fmaxf(fmaxf(fmaxf(l[4 * j], l[4 * j + 1]), fmaxf(l[4 * j + 2], l[4 * j + 3])), mx);
+      for (int j = 0; j < kMaxPerLane / 4; ++j) {
+        if (j * 4 < per_lane) {
+          float4 q = row[j * 32 + lane];
+          // torch's CUDA `tensor / python_float` multiplies by the fp32 reciprocal (BinaryDivTrueKernel.cu)
+          l[4 * j + 0] = __fmul_rn(q.x, inv_temp); l[4 * j + 1] = __fmul_rn(q.y, inv_temp);
+          l[4 * j + 2] = __fmul_rn(q.z, inv_temp); l[4 * j + 3] = __fmul_rn(q.w, inv_temp);
+          mx = fmaxf(fmaxf(fmaxf(l[4 * j], l[4 * j + 1]), fmaxf(l[4 * j + 2], l[4 * j + 3])), mx);
+        }
+      }
+    } else {
+      const float* row = logits + tok * (int64_t)K;
+#pragma unroll
+      for (int j = 0; j < kMaxPerLane; ++j) {
+        if (j < per_lane) {
+          const int k = j * 32 + lane;
+          l[j] = k < K ? __fmul_rn(row[k], inv_temp) : -INFINITY;
+          mx = fmaxf(mx, l[j]);
+        }
       }
     }
 #pragma unroll
@@ -179,7 +193,8 @@ __global__ void __launch_bounds__(256) sample_step_kernel(const float* __restric
 #pragma unroll
     for (int j = 0; j < kMaxPerLane; ++j) {
       if (j < per_lane) {
-        const int k = (j >> 2) * 128 + lane * 4 + (j & 3);
+        const int k = VEC ? (j >> 2) * 128 + lane * 4 + (j & 3) : j * 32 + lane;
+        if (!VEC && k >= K) continue;
         const float p = __fdiv_rn(l[j], s2);
         uint32_t r = r0 + (uint32_t)k;
         uint64_t qq = q0;
@@ -267,8 +282,7 @@ static int sample_step_impl(const float* logits, int64_t* x_t, uint8_t* unmasked
                             uint64_t offset_exponential, int64_t token_base, int64_t n_tokens_global,
                             const uint64_t* rng_dev, void* stream) {
   SD_REQUIRE(n_tokens >= 0 && token_base >= 0 && n_tokens_global >= token_base + n_tokens, "sample_step: bad token range");
-  SD_REQUIRE(K >= 32 && K % 128 == 0 && K <= 32 * kMaxPerLaneAll, "sample_step: K=%d must be a multiple of 128 in [128, %d]", K,
-             32 * kMaxPerLaneAll);
+  SD_REQUIRE(K >= 1 && K <= 32 * kMaxPerLaneAll, "sample_step: K=%d must be in [1, %d]", K, 32 * kMaxPerLaneAll);
   SD_REQUIRE(t >= 1, "sample_step: t must be >= 1");
   SD_REQUIRE(temp > 0.f, "sample_step: temperature must be positive");
   SD_REQUIRE(offset_uniform % 4 == 0 && offset_exponential % 4 == 0, "sample_step: offsets must be multiples of 4");
@@ -284,13 +298,20 @@ static int sample_step_impl(const float* logits, int64_t* x_t, uint8_t* unmasked
   ce.offset4 = offset_exponential / 4;
   const float inv_t = 1.0f / (float)t;  // `1 / t_mask.float()`  (vq_diffusion.py:118)
   int64_t blocks = (n_tokens * 32 + 255) / 256;
-#define SD_SAMPLE_LAUNCH(PL)                                                                                  \
-  sample_step_kernel<PL><<<grid_cap(blocks), 256, 0, as_stream(stream)>>>(logits, x_t, unmasked, x0_hat, n_tokens, K, \
-                                                                          inv_t, 1.0f / temp, cu, ce, token_base, rng_dev)
-  if (K <= 128) SD_SAMPLE_LAUNCH(4);
-  else if (K <= 256) SD_SAMPLE_LAUNCH(8);
-  else if (K <= 512) SD_SAMPLE_LAUNCH(16);
-  else SD_SAMPLE_LAUNCH(32);
+#define SD_SAMPLE_LAUNCH(PL, VEC)                                                                                  \
+  sample_step_kernel<PL, VEC><<<grid_cap(blocks), 256, 0, as_stream(stream)>>>(logits, x_t, unmasked, x0_hat, n_tokens, K, \
+                                                                               inv_t, 1.0f / temp, cu, ce, token_base, rng_dev)
+  if (K % 128 == 0 && (((uintptr_t)logits) & 15) == 0) {
+    if (K <= 128) SD_SAMPLE_LAUNCH(4, true);
+    else if (K <= 256) SD_SAMPLE_LAUNCH(8, true);
+    else if (K <= 512) SD_SAMPLE_LAUNCH(16, true);
+    else SD_SAMPLE_LAUNCH(32, true);
+  } else {   // any codebook size (the reference's --codebook_size is free, R/main.py:58)
+    if (K <= 128) SD_SAMPLE_LAUNCH(4, false);
+    else if (K <= 256) SD_SAMPLE_LAUNCH(8, false);
+    else if (K <= 512) SD_SAMPLE_LAUNCH(16, false);
+    else SD_SAMPLE_LAUNCH(32, false);
+  }
 #undef SD_SAMPLE_LAUNCH
   SD_LAUNCH_CHECK();
   return SD_OK;

@@ -40,6 +40,7 @@ def ours(kind, numel, seed, offset, base=0, n=None):
 @pytest.mark.parametrize("numel", [1, 49, 256 * 49, 303104 * 4 + 17, 256 * 49 * 128, 3_000_001])
 def test_uniform_and_exponential_match_torch_cuda(numel):
     sms, thr = dev_info()
+    torch.cuda.init()   # default_generators is empty until CUDA is initialised (this may be the first test to run)
     gen = torch.cuda.default_generators[torch.cuda.current_device()]
     torch.manual_seed(1234)
     assert gen.get_offset() == 0
@@ -63,7 +64,8 @@ def test_uniform_and_exponential_match_torch_cuda(numel):
         assert torch.equal(part, ref_u[777:977])
 
 
-@pytest.mark.parametrize("K,temp", [(128, 1.0), (128, 0.65), (512, 0.3), (1024, 1.0)])
+@pytest.mark.parametrize("K,temp", [(128, 1.0), (128, 0.65), (512, 0.3), (1024, 1.0), (32, 1.0), (96, 0.8), (200, 1.0),
+                                    (1000, 0.65)])
 def test_sample_step_matches_torch_categorical(K, temp):
     """Same logits, same seed: our fused step draws the same tokens as the reference's torch code path
     (rand_like -> Categorical(logits/temp).sample(), vq_diffusion.py:118-140)."""
