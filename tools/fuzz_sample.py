@@ -26,7 +26,7 @@ def main():
     for case in range(n_cases):
         T = rng.choice([1, 2, 4, 8])
         hw = rng.choice([4, 5, 7, 8])
-        K = rng.choice([32, 128, 512])
+        K = rng.choice([32, 48, 100, 128, 200, 512, 1000])
         b = rng.choice([1, 2, 3, 5, 8])
         temp = rng.choice([0.65, 0.9, 1.0])
         steps = rng.choice([hw * hw, hw * hw, max(3, hw * hw // 3)])
