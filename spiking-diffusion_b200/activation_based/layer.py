@@ -63,8 +63,9 @@ class _ConvFn(torch.autograd.Function):
             if transposed:   # adjoint of conv_transpose2d(x, w) is conv2d(gy, w): w [C_in, C_out, k, k] read as [out, in, k, k]
                 spec = _ConvSpec(weight.detach(), False, ks, stride, padding, (0, 0))
             else:            # adjoint of conv2d(x, w) is conv_transpose2d(gy, w) sized back to the input
-                op = d.H_in - ((d.H_out - 1) * stride[0] - 2 * padding[0] + ks[0])
-                spec = _ConvSpec(weight.detach(), True, ks, stride, padding, (op, op))
+                op_h = d.H_in - ((d.H_out - 1) * stride[0] - 2 * padding[0] + ks[0])
+                op_w = d.W_in - ((d.W_out - 1) * stride[1] - 2 * padding[1] + ks[1])
+                spec = _ConvSpec(weight.detach(), True, ks, stride, padding, (op_h, op_w))
             adj = engine.FusedLayer(spec, None, None, T=d.T, B=d.B, H_in=d.H_out, W_in=d.W_out, in_kind=_lib.IN_REAL_SEQ,
                                     out_kind=_lib.OUT_REAL_SEQ, impl="simt")
             gx = adj.run(gy, adj.alloc_out())

@@ -81,9 +81,9 @@ class FusedLayer:
             raise ValueError("dilation/groups other than 1 are not supported")
         if transposed:
             C_in, C_out = w.shape[0], w.shape[1]
-            op = conv.output_padding[0]
-            H_out = (H_in - 1) * stride - 2 * pad + kh + op
-            W_out = (W_in - 1) * stride - 2 * pad + kw + op
+            op_h, op_w = conv.output_padding[0], conv.output_padding[1]
+            H_out = (H_in - 1) * stride - 2 * pad + kh + op_h
+            W_out = (W_in - 1) * stride - 2 * pad + kw + op_w
         else:
             C_out, C_in = w.shape[0], w.shape[1]
             H_out = (H_in + 2 * pad - kh) // stride + 1
