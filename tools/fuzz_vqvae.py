@@ -21,6 +21,7 @@ def main():
     for case in range(n_cases):
         T = rng.choice([1, 2, 4, 4, 8, 16])
         size = rng.choice([8, 12, 16, 20, 24, 28, 28, 32])
+        size_w = size if rng.random() < 0.5 else rng.choice([8, 12, 16, 20, 24, 28, 32])   # non-square half of the time
         in_dim = rng.choice([1, 1, 3])
         K = rng.choice([64, 128, 512])
         B = rng.choice([1, 2, 3, 5, 9, 17, 33])
@@ -29,11 +30,11 @@ def main():
         functional.set_step_mode(m, "m")
         m.load_state_dict(sd)
         m = m.eval().cuda()
-        img = synth.synth_images(case, B, in_dim=in_dim, size=size)
+        img = synth.synth_images(case, B, in_dim=in_dim, size=max(size, size_w))[..., :size, :size_w].contiguous()
         xs = img.unsqueeze(0).repeat(T, 1, 1, 1, 1)
         tr = O.Trace()
         e_ref, rec_ref, idx_ref = O.vqvae_forward_eval(xs, sd, trace=tr)
-        plan = m.plan(T, B, size, size)
+        plan = m.plan(T, B, size, size_w)
         e, rec, idx = plan.forward(img.cuda(), const_over_T=True)
         margin = O.vq_margin(tr["feat"].reshape(-1, 16), sd["vq_layer.embeddings.weight"])
         hard_idx = int(((idx.cpu() != idx_ref) & (margin > 1e-4)).sum())
@@ -46,7 +47,7 @@ def main():
         same = torch.equal(idx2, idx) and float((rec2 - rec).abs().max()) <= 1e-6
         ok = hard_idx == 0 and flips <= 1e-3 and err <= 1e-3 and same
         bad += not ok
-        print(f"case {case}: T={T} {in_dim}x{size}x{size} K={K} B={B} tc_enc={plan.tc_encoder} tc_dec={plan.tc_decoder}: "
+        print(f"case {case}: T={T} {in_dim}x{size}x{size_w} K={K} B={B} tc_enc={plan.tc_encoder} tc_dec={plan.tc_decoder}: "
               f"index mismatches outside margin {hard_idx}, generator flip rate {flips:.1e}, image mean-abs err {err:.1e}, "
               f"module==plan {same}", "" if ok else "<-- CHECK", flush=True)
     print("suspicious cases:", bad)
