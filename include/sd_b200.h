@@ -113,7 +113,8 @@ int sd_memout(const float* x, float* out, const float* coef_host, int T, int64_t
  *   z = (1-alpha)*memout(x) + alpha*sum_t x / T, written NHWC-flat as fp32 [B*H*W, D].
  *   spikes: STF [T][D/8][R_alloc][8].
  * sd_vq_lookup replaces get_code_indices (vae_model.py:87-95): argmin_k (|z|^2 + |e_k|^2) - 2 z.e_k,
- *   first index on ties.  z: fp32 [M, D], codebook: fp32 [K, D], idx: int64 [M].
+ *   first index on ties.  z: fp32 [M, D], codebook: fp32 [K, D], idx: int64 [M].  Any D >= 1 (8 / 16 / 32 use a
+ *   register-blocked kernel).
  *   margin_or_null: optional fp32 [M], second-best minus best distance.
  * sd_vq_gather replaces quantize + permute(0,3,1,2) (vae_model.py:97-99, :54): idx int64 [B*H*W] ->
  *   fp32 [B, D, H, W].

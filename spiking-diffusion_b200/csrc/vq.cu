@@ -125,6 +125,49 @@ __global__ void __launch_bounds__(kVqWarps * 32) vq_lookup_kernel(const float* _
   }
 }
 
+// Any embedding dimension (the reference's --embedding_dim is free; 8 / 16 / 32 use the register-blocked kernel above):
+// one warp per token, lanes over the codes, the same arithmetic order (sequential |z|^2 and |e|^2, FMA dot product,
+// (|z|^2 + |e|^2) - 2 z.e, first index on ties).
+__global__ void __launch_bounds__(256) vq_lookup_generic_kernel(const float* __restrict__ z, const float* __restrict__ cb,
+                                                                int64_t* __restrict__ idx, float* __restrict__ margin,
+                                                                int64_t M, int D, int K) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t m = warp_global; m < M; m += n_warps) {
+    const float* zr = z + m * D;
+    float zz = 0.f;
+    for (int d = 0; d < D; ++d) zz = __fadd_rn(zz, __fmul_rn(zr[d], zr[d]));
+    float b = INFINITY, s2 = INFINITY;
+    int bi = 0;
+    for (int k = lane; k < K; k += 32) {
+      const float* e = cb + (int64_t)k * D;
+      float ee = 0.f, dot = 0.f;
+      for (int d = 0; d < D; ++d) {
+        ee = __fadd_rn(ee, __fmul_rn(e[d], e[d]));
+        dot = fmaf(zr[d], e[d], dot);
+      }
+      const float dist = __fsub_rn(__fadd_rn(zz, ee), __fmul_rn(2.0f, dot));
+      if (dist < b) { s2 = b; b = dist; bi = k; }
+      else if (dist < s2) { s2 = dist; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      float ob = __shfl_xor_sync(0xffffffffu, b, off);
+      float os = __shfl_xor_sync(0xffffffffu, s2, off);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      bool take = (ob < b) || (ob == b && oi < bi);
+      float loser = take ? b : ob;
+      if (take) { b = ob; bi = oi; }
+      s2 = fminf(fminf(s2, os), loser);
+    }
+    if (lane == 0) {
+      idx[m] = bi;
+      if (margin) margin[m] = s2 - b;
+    }
+  }
+}
+
 __global__ void vq_gather_kernel(const int64_t* __restrict__ idx, const float* __restrict__ cb,
                                  float* __restrict__ out, int B, int D, int H, int W, int K) {
   const int64_t total = (int64_t)B * D * H * W;
@@ -181,8 +224,9 @@ int sd_vq_lookup(const float* z, const float* codebook, int64_t* idx, float* mar
     case 16: vq_lookup_kernel<16><<<grid, kVqWarps * 32, 0, st>>>(z, codebook, idx, margin, M, K); break;
     case 32: vq_lookup_kernel<32><<<grid, kVqWarps * 32, 0, st>>>(z, codebook, idx, margin, M, K); break;
     default:
-      set_error("vq_lookup: embedding_dim %d not built (8, 16, 32)", D);
-      return SD_ERR_UNSUPPORTED;
+      SD_REQUIRE(D >= 1, "vq_lookup: bad embedding_dim %d", D);
+      vq_lookup_generic_kernel<<<grid_cap((M * 32 + 255) / 256), 256, 0, st>>>(z, codebook, idx, margin, M, D, K);
+      break;
   }
   SD_LAUNCH_CHECK();
   return SD_OK;
