@@ -84,3 +84,20 @@ def test_stf_round_trip(shape):
     stf = engine.stf_from_nchw(x)
     assert torch.equal(engine.stf_to_nchw(stf, T, B, C, H, W), x)
     assert float(stf.float().sum()) == float(x.sum())          # guard rows / padded channels are zero
+
+
+@pytest.mark.parametrize("T", [8, 16])
+def test_multi_pass_shards_equal_the_whole_batch_across_pass_modes(T):
+    """T = 8 / 16 layers run as fused passes or, for small shards, as T-parallel passes plus a separate LIF kernel; which
+    one is chosen depends on the shard size and the layer.  Ragged shards must still reproduce the whole batch bit for
+    bit (same K order, same LIF arithmetic)."""
+    K, b = 128, 100
+    den, _ = make_denoiser(T, K, seed=4)
+    whole = AbsorbingDiffusion(den, mask_id=K, shape=(7, 7), n_samples=b).sample(temp=0.8, sample_steps=20, seed=21)
+    parts, lo = [], 0
+    for n in (7, 33, 60):
+        a = AbsorbingDiffusion(den, mask_id=K, shape=(7, 7), n_samples=n)
+        parts.append(a.sample(temp=0.8, sample_steps=20, seed=21, n_global=b, shard_base=lo))
+        lo += n
+    assert torch.equal(torch.cat(parts), whole)
+    assert int(whole.max()) < K
