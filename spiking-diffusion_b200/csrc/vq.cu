@@ -213,7 +213,7 @@ int sd_vq_feature(const void* spikes_stf, const float* alpha_dev, const float* c
 
 int sd_vq_lookup(const float* z, const float* codebook, int64_t* idx, float* margin, int64_t M, int D, int K,
                  void* stream) {
-  SD_REQUIRE(M >= 0 && K >= 1, "vq_lookup: bad M=%lld K=%d", (long long)M, K);
+  SD_REQUIRE(M >= 0 && K >= 1 && D >= 1, "vq_lookup: bad M=%lld D=%d K=%d", (long long)M, D, K);
   if (M == 0) return SD_OK;
   SD_REQUIRE(z && codebook && idx, "null pointer argument");
   SD_DEVICE_OR_RETURN();
@@ -224,7 +224,6 @@ int sd_vq_lookup(const float* z, const float* codebook, int64_t* idx, float* mar
     case 16: vq_lookup_kernel<16><<<grid, kVqWarps * 32, 0, st>>>(z, codebook, idx, margin, M, K); break;
     case 32: vq_lookup_kernel<32><<<grid, kVqWarps * 32, 0, st>>>(z, codebook, idx, margin, M, K); break;
     default:
-      SD_REQUIRE(D >= 1, "vq_lookup: bad embedding_dim %d", D);
       vq_lookup_generic_kernel<<<grid_cap((M * 32 + 255) / 256), 256, 0, st>>>(z, codebook, idx, margin, M, D, K);
       break;
   }

@@ -84,3 +84,36 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "snn_oracle" not in text, f
+
+
+def test_argument_checks_of_the_layout_and_training_entry_points():
+    """Bad arguments are rejected on the host, before any device work (SD_ERR_INVALID -> ValueError), with a message."""
+    import ctypes
+    L = _lib.lib()
+    buf = torch.zeros(64)
+    p = buf.data_ptr()
+    for rc in (L.sd_stf_upsample2x(p, p, 4, 1, 8, 7, 7, None),            # aliased in / out
+               L.sd_stf_upsample2x(None, p, 4, 1, 8, 7, 7, None),         # null input
+               L.sd_stf_subsample2x(p, p + 16, 0, 1, 8, 7, 7, None),      # T = 0
+               L.sd_stf_subsample2x(p + 4, p + 32, 1, 1, 8, 2, 2, None),  # misaligned
+               L.sd_bn_local_stats(p, p, None, 1, 1, 1, None),            # null output
+               L.sd_bn_backward_reduce(p, p, p, p, p, p, 0, 1, 1, 1e-5, None),
+               L.sd_bn_backward_apply(p, p, p, p, None, None, p, p, 1, 1, 1, 1e-5, None),
+               L.sd_sample_step(p, p, p, None, 4, 2000, 1, 1.0, 0, 0, 0, 0, 4, None),   # K beyond 1024
+               L.sd_sample_step(p, p, p, None, 4, 128, 0, 1.0, 0, 0, 0, 0, 4, None),    # t = 0
+               L.sd_vq_lookup(p, p, p, None, 4, 0, 8, None)):                           # D = 0
+        assert rc == _lib.SD_ERR_INVALID, L.sd_last_error()
+        assert len(L.sd_last_error()) > 0
+        with pytest.raises(ValueError):
+            _lib.check(rc)
+    d = _lib.ConvDesc()
+    assert L.sd_conv_wgrad_workspace_bytes(ctypes.byref(d)) == 0           # invalid descriptor: nothing to allocate
+    assert L.sd_conv_wgrad(ctypes.byref(d), p, p, p, None, p, None) == _lib.SD_ERR_INVALID
+    d.T, d.B, d.C_in, d.H_in, d.W_in, d.C_out, d.H_out, d.W_out = 2, 3, 8, 7, 7, 16, 7, 7
+    d.kh = d.kw = 3
+    d.stride = d.pad = 1
+    d.in_kind, d.out_kind, d.in_T, d.C_in0 = _lib.IN_REAL_SEQ, _lib.OUT_REAL_SEQ, 2, 8
+    d.tau, d.v_threshold, d.hard_reset, d.nsplit = 2.0, 1.0, 1, 2
+    ws = L.sd_conv_wgrad_workspace_bytes(ctypes.byref(d))
+    assert ws >= 9 * 8 * 16 * 4 and ws % (9 * 8 * 16 * 4) == 0             # splits x taps x C_in x C_out floats
+    assert L.sd_conv_wgrad(ctypes.byref(d), p, p, p, None, None, None) == _lib.SD_ERR_INVALID   # workspace missing
