@@ -8,6 +8,7 @@ and runs each as ONE fused kernel, with spike tensors staying in the packed STF 
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from typing import List, Optional, Tuple
 
@@ -72,7 +73,6 @@ class _ConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
             gw = torch.empty_like(weight, dtype=torch.float32)
             gb = torch.empty(d.C_out, dtype=torch.float32, device=gy.device) if has_bias else None
-            import ctypes
             ws = torch.empty(lib().sd_conv_wgrad_workspace_bytes(ctypes.byref(d)), dtype=torch.uint8, device=gy.device)
             check(lib().sd_conv_wgrad(ctypes.byref(d), ptr(x5), ptr(gy), ptr(gw), ptr(gb), ptr(ws), stream_ptr()))
         return gx, gw, gb, None

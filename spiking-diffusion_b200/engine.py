@@ -12,6 +12,7 @@ stream.  PyTorch is used for device memory and streams only.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, Optional
 
 import torch
@@ -249,7 +250,6 @@ def plan_sub_batches(b: int, rows_per_image: int, n_streams: Optional[int] = Non
        there); below 64 images sub-batches would only add launches;
      * sub-batch sizes are cut so that their row count ends just below a multiple of 256: no half-empty pair.
     ``n_streams`` (or env SD_SAMPLER_STREAMS) overrides the count; the alignment rule still applies."""
-    import os
     total_pairs = -(-b * rows_per_image // 256)
     if n_streams is None:
         env = os.environ.get("SD_SAMPLER_STREAMS")
@@ -370,7 +370,6 @@ class SamplerPlan:
         use_graph (default: env SD_SAMPLER_GRAPH, on): the loop (h*w steps x 8 kernels x sub-batches) is captured once
         per (temp, steps) into a CUDA graph and replayed; the Philox (seed, offset) pair lives in device memory
         (sd_sample_step_dev) so every replay draws a fresh, torch-identical stream."""
-        import os
         import numpy as np
         if use_graph is None:
             use_graph = os.environ.get("SD_SAMPLER_GRAPH", "1") != "0"
@@ -457,7 +456,6 @@ class VQVAEPlan:
         self.e1c = mk(enc[0], enc[1], enc[2], H, W, in_kind=_lib.IN_REAL_CONST, out_kind=_lib.OUT_LIF, impl="simt")
         # enc.conv2 (stride 2, spike input): on the tcgen05 kernel at stride 1, even positions kept afterwards
         # (4x the MMAs of the algorithm, several times faster than CUDA cores); SD_ENCODER_TC=0 keeps the CUDA-core kernel
-        import os
         self.tc_encoder = (os.environ.get("SD_ENCODER_TC", "1") != "0" and _Stride1Conv.eligible(enc[3])
                            and self.e1.W_out + 2 <= 64)
         if self.tc_encoder:
@@ -477,7 +475,6 @@ class VQVAEPlan:
         # Decoder: the two stride-2 transposed convolutions run on the tcgen05 kernel as stride-1 convolutions of the
         # zero-inserted upsampled spikes (4x the MMAs of the algorithm, still several times faster than CUDA cores);
         # SD_DECODER_TC=0 keeps the CUDA-core kernels (used by the tests to cross-check the two paths).
-        import os
         self.tc_decoder = (os.environ.get("SD_DECODER_TC", "1") != "0" and _UpsampledConvT.eligible(dec[0])
                            and _UpsampledConvT.eligible(dec[3]) and 4 * self.w + 2 <= 64)
         if self.tc_decoder:
