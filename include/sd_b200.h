@@ -205,9 +205,13 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream);
 /* 1 if sd_conv_lif_tc supports the descriptor on this build. */
 int sd_conv_tc_supported(const sd_conv_desc* d);
 /* Diagnostics (tools/trace_tc.py): while `buf` (device memory, >= grid * 64 int64) is set, sd_conv_lif_tc launches
- * write per-CTA cycle stamps of the MMA and epilogue warps to it.  Pass NULL to switch tracing off.  No reference
- * counterpart. */
+ * write per-CTA cycle stamps of the MMA and epilogue warps to it.  Pass NULL to switch tracing off.  Only the
+ * -DSD_TRACE build of the library carries the stamps (the shipped kernel has no diagnostics code); the shipped library
+ * returns SD_ERR_UNSUPPORTED for a non-NULL buffer.  No reference counterpart. */
 int sd_debug_tc_trace(void* buf);
+/* Diagnostics (tools/bench_layers.py): the SD_TC_* tile-shape knobs are read from the environment once per process;
+ * this re-reads them.  No reference counterpart. */
+int sd_debug_tc_reload_knobs(void);
 
 /* ---- (f.1) training-path kernels (fp32 on CUDA cores: tiled implicit GEMMs) -------------------------------------
  * The reference trains through torch autograd over F.conv2d / F.conv_transpose2d / F.batch_norm

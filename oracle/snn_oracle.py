@@ -324,8 +324,11 @@ def sample(p: Params, T: int, b: int, hw: Tuple[int, int], K: int, mask_id: int,
         q = exponential_fn(step, b * h * w, K)
         x0_hat = torch.argmax(probs / q, dim=-1).reshape(b, h, w).unsqueeze(1)
         if record is not None:
-            record.append({"t": t, "changes": changes.clone(), "logits": logits.clone(), "x0_hat": x0_hat.clone()})
+            record.append({"t": t, "changes": changes.clone(), "logits": logits.clone(), "x0_hat": x0_hat.clone(),
+                           "probs": probs, "q": q})
         x_t[changes] = x0_hat[changes]
+        if record is not None:
+            record[-1]["x_t"] = x_t.clone()     # token grid after this step (trajectory comparison)
     return x_t
 
 

@@ -25,7 +25,7 @@ SYMBOLS = [
     "sd_last_error", "sd_version", "sd_device_info", "sd_stf_guard", "sd_stf_rows", "sd_stf_bytes",
     "sd_stf_from_nchw", "sd_stf_to_nchw", "sd_stf_upsample2x", "sd_stf_subsample2x", "sd_channel_affine", "sd_state_convert", "sd_lif_forward", "sd_lif_backward", "sd_memout", "sd_vq_feature", "sd_vq_lookup",
     "sd_vq_gather", "sd_conv_weight_bytes_simt", "sd_conv_weight_bytes_tc", "sd_conv_workspace_bytes", "sd_conv_weight_layout_tc", "sd_conv_pack_weights_simt",
-    "sd_conv_pack_weights_tc", "sd_conv_lif_simt", "sd_conv_lif_tc", "sd_conv_tc_supported", "sd_debug_tc_trace", "sd_conv_wgrad_workspace_bytes", "sd_conv_wgrad",
+    "sd_conv_pack_weights_tc", "sd_conv_lif_simt", "sd_conv_lif_tc", "sd_conv_tc_supported", "sd_debug_tc_trace", "sd_debug_tc_reload_knobs", "sd_conv_wgrad_workspace_bytes", "sd_conv_wgrad",
     "sd_bn_train_forward", "sd_bn_backward", "sd_bn_local_stats", "sd_bn_backward_reduce", "sd_bn_backward_apply", "sd_philox_uniform",
     "sd_philox_exponential", "sd_philox_offset_increment", "sd_sample_step", "sd_sample_step_dev", "sd_denoiser_input", "sd_to_uint8",
 ]
@@ -50,15 +50,30 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu for sm_100a into spiking-diffusion_b200/libsd_b200.so (in-tree, travels with gpurun)."""
+TRACE_LIB_PATH = os.path.join(ROOT, "build", "libsd_b200_trace.so")
+
+
+def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into spiking-diffusion_b200/libsd_b200.so (in-tree, travels with gpurun).
+
+    ``trace=True`` builds the diagnostics variant instead (-DSD_TRACE: cycle stamps and the SD_TC_DBG experiment
+    paths inside conv3x3_tc_kernel) as build/libsd_b200_trace.so; select it with the environment variable
+    SD_B200_LIB before the first call (tools/trace_tc.py does).  The shipped library carries none of that code."""
+    if trace:
+        return _build_to(TRACE_LIB_PATH, os.path.join(ROOT, "build", "trace_obj"), ["-DSD_TRACE"], verbose)
     if not force and not _stale():
         return LIB_PATH
+    return _build_to(LIB_PATH, CSRC, [], verbose)
+
+
+def _build_to(lib_path: str, obj_dir: str, extra_flags, verbose: bool) -> str:
+    os.makedirs(obj_dir, exist_ok=True)
+    os.makedirs(os.path.dirname(lib_path), exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:
@@ -67,11 +82,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out.strip():
             print(out)
-    cmd = [_nvcc(), "--shared", "-cudart", "shared", "-o", LIB_PATH] + objs
+    cmd = [_nvcc(), "--shared", "-cudart", "shared", "-o", lib_path] + objs
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
-    return LIB_PATH
+    return lib_path
 
 
 class ConvDesc(ctypes.Structure):
@@ -130,6 +145,7 @@ def _declare(lib: ctypes.CDLL) -> None:
         "sd_conv_lif_tc": (i, [pd, pa, vp]),
         "sd_conv_tc_supported": (i, [pd]),
         "sd_debug_tc_trace": (i, [vp]),
+        "sd_debug_tc_reload_knobs": (i, []),
         "sd_conv_wgrad_workspace_bytes": (i64, [pd]),
         "sd_conv_wgrad": (i, [pd, vp, vp, vp, vp, vp, vp]),
         "sd_bn_train_forward": (i, [vp, vp, vp, vp, vp, vp, i64, i, i64, f, vp]),
@@ -156,10 +172,11 @@ def lib() -> ctypes.CDLL:
     """The loaded C-ABI library.  Raises if it has not been built (no silent fallback)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise SdError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+        path = os.environ.get("SD_B200_LIB") or LIB_PATH   # SD_B200_LIB: the -DSD_TRACE diagnostics build (tools/)
+        if not os.path.exists(path):
+            raise SdError(f"{path} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(there is no CPU or PyTorch fallback for the CUDA path)")
-        _lib = ctypes.CDLL(LIB_PATH)
+        _lib = ctypes.CDLL(path)
         _declare(_lib)
     return _lib
 
@@ -175,10 +192,77 @@ def check(rc: int) -> None:
     raise SdError(f"libsd_b200 error {rc}: {msg}")
 
 
-def stream_ptr() -> int:
-    import torch
-    return torch.cuda.current_stream().cuda_stream
+# ---- device discipline ---------------------------------------------------------------------------------------------
+# The C-ABI takes raw pointers and a raw stream and launches on the CUDA runtime's CURRENT device.  Every call site
+# builds its arguments with ptr(tensor) ... stream_ptr() (the stream is always the last argument), so the two helpers
+# also enforce that all tensors of one call live on one device and that this device is the current one; the public
+# entry points (module forward methods, plans) run under ``on_device_of`` so that a model moved with ``.to('cuda:1')``
+# works without the caller touching torch.cuda.set_device.
+import threading
+
+_tls = threading.local()
 
 
 def ptr(t) -> Optional[int]:
-    return None if t is None else t.data_ptr()
+    if t is None:
+        return None
+    if t.is_cuda:
+        seen = getattr(_tls, "devices", None)
+        if seen is None:
+            seen = _tls.devices = set()
+        seen.add(t.device.index)
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+    seen = getattr(_tls, "devices", None)
+    cur = torch.cuda.current_device()
+    if seen:
+        devs = sorted(seen)
+        seen.clear()
+        if len(devs) > 1:
+            raise ValueError(f"all tensors of one libsd_b200 call must live on one CUDA device, got cuda:{devs}")
+        if devs[0] != cur:
+            raise RuntimeError(f"tensors live on cuda:{devs[0]} but the current CUDA device is cuda:{cur}; "
+                               "run the call under torch.cuda.device(tensor.device) (the public entry points do)")
+    return torch.cuda.current_stream(cur).cuda_stream
+
+
+def first_cuda_device(*objs):
+    """Device of the first CUDA tensor found among tensors / modules / sequences of them, or None."""
+    import torch
+    for o in objs:
+        if isinstance(o, torch.Tensor):
+            if o.is_cuda:
+                return o.device
+        elif isinstance(o, torch.nn.Module):
+            for t in o.parameters():
+                if t.is_cuda:
+                    return t.device
+                break
+            for t in o.buffers():
+                if t.is_cuda:
+                    return t.device
+                break
+        elif isinstance(o, (list, tuple)):
+            d = first_cuda_device(*o)
+            if d is not None:
+                return d
+    return None
+
+
+def on_device_of(fn):
+    """Decorator for public entry points: run ``fn`` with the CUDA device of its first CUDA tensor / module argument
+    current (torch.cuda.device), so kernels, streams and allocations all land on the data's device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        import torch
+        dev = first_cuda_device(*args, *kwargs.values())
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper

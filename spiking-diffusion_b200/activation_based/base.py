@@ -11,6 +11,8 @@ import copy
 import torch
 import torch.nn as nn
 
+from .._lib import on_device_of as _on_device_of
+
 
 class StepModule:
     def supported_step_mode(self):
@@ -37,6 +39,20 @@ class LazyState:
 
     def materialize(self):
         return self._fn()
+
+
+class ConsumedState(LazyState):
+    """Marks a LIF state that a fused whole-network kernel chain consumed without writing it back (the denoiser's
+    plan keeps membrane potentials in registers / L2 only).  The reference would continue from the carried state on
+    the next forward; here that is impossible, so reading the state or calling forward again raises until
+    ``reset()`` (``functional.reset_net``) -- which every reference call site issues -- clears the mark."""
+
+    def __init__(self, what: str):
+        self._what = what
+
+    def materialize(self):
+        raise RuntimeError(f"the LIF state of {self._what} was consumed inside the fused kernels of the last forward; "
+                           "call functional.reset_net(model) before reading it or running another forward")
 
 
 class MemoryModule(nn.Module, StepModule):
@@ -69,6 +85,7 @@ class MemoryModule(nn.Module, StepModule):
         ys = [self.single_step_forward(x_seq[t], *args, **kwargs).unsqueeze(0) for t in range(x_seq.shape[0])]
         return torch.cat(ys, 0)
 
+    @_on_device_of
     def forward(self, *args, **kwargs):
         if self.step_mode == "s":
             return self.single_step_forward(*args, **kwargs)
@@ -117,13 +134,16 @@ class MemoryModule(nn.Module, StepModule):
 
     def _resolve_lazy(self):
         for key, value in self._memories.items():
-            if isinstance(value, LazyState):
+            if isinstance(value, LazyState) and not isinstance(value, ConsumedState):
                 self._memories[key] = value.materialize()
 
     def __getstate__(self):
         # pickling / torch.save(module): closures of lazy states do not pickle, tensors do
         self._resolve_lazy()
-        return self.__dict__
+        state = dict(self.__dict__)
+        state["_memories"] = {k: (copy.deepcopy(self._memories_rv[k]) if isinstance(v, ConsumedState) else v)
+                              for k, v in self._memories.items()}
+        return state
 
     def memory_is_reset(self, name: str) -> bool:
         """True if the memory still holds its (non-tensor) reset value; does not materialise a lazy state."""

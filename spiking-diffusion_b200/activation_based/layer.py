@@ -207,6 +207,7 @@ class Conv2d(nn.Conv2d, _ConvMixin):
     def extra_repr(self):
         return super().extra_repr() + f", step_mode={self.step_mode}"
 
+    @_lib.on_device_of
     def forward(self, x: torch.Tensor):
         return self._forward_any(x)
 
@@ -221,6 +222,7 @@ class ConvTranspose2d(nn.ConvTranspose2d, _ConvMixin):
     def extra_repr(self):
         return super().extra_repr() + f", step_mode={self.step_mode}"
 
+    @_lib.on_device_of
     def forward(self, x: torch.Tensor):
         return self._forward_any(x)
 
@@ -233,6 +235,7 @@ class BatchNorm2d(nn.BatchNorm2d, base.StepModule):
     def extra_repr(self):
         return super().extra_repr() + f", step_mode={self.step_mode}"
 
+    @_lib.on_device_of
     def forward(self, x: torch.Tensor):
         if not x.is_cuda:
             raise RuntimeError("layer forward needs CUDA tensors: spiking_diffusion_b200 has no CPU path")
@@ -323,6 +326,19 @@ class SpikingSequential(nn.Sequential):
             h, w = fl.H_out, fl.W_out
         return stages, plans
 
+    def invalidate_plans(self) -> None:
+        """Drop the cached fused plan (packed weights, folded BN).  The cache key covers parameter / buffer versions and
+        the LIF / BN hyper-parameters, but NOT in-place edits through ``.data`` (they do not bump ``_version``)."""
+        self._key = None
+
+    def __getstate__(self):
+        # plans hold ctypes pointers / device buffers: never pickled or deep-copied, rebuilt on the next forward
+        state = dict(self.__dict__)
+        for k in ("_key", "_stage_list", "_plans", "_bufs"):
+            state.pop(k, None)
+        return state
+
+    @_lib.on_device_of
     def forward(self, x: torch.Tensor):
         if not x.is_cuda:
             raise RuntimeError("SpikingSequential.forward needs CUDA tensors: spiking_diffusion_b200 has no CPU path")
@@ -334,8 +350,7 @@ class SpikingSequential(nn.Sequential):
                 x = m(x)
             return x
         T, B, _, H, W = x.shape
-        key = (T, B, H, W, x.device, tuple(p._version for p in self.parameters()),
-               tuple(b._version for b in self.buffers()))
+        key = (T, B, H, W) + engine.module_cache_key(self)
         if getattr(self, "_key", None) != key:
             self._stage_list, self._plans = self._build(T, B, H, W, x.device)
             self._bufs = [p.alloc_out() for p in self._plans]

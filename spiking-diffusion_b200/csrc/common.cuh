@@ -10,7 +10,8 @@
 namespace sd {
 
 void set_error(const char* fmt, ...);
-int check_device();  // SD_OK or SD_ERR_NO_DEVICE (cached per process)
+int check_device();  // SD_OK or SD_ERR_NO_DEVICE for the CURRENT device (cached per device)
+int current_device_index();
 int sm_count();
 int max_threads_per_sm();
 int validate_conv_desc(const sd_conv_desc* d);  // SD_OK or SD_ERR_INVALID (conv_simt.cu)

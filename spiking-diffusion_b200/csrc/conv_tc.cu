@@ -98,7 +98,7 @@ struct TcParams {
   int dbg;                  // diagnostics (env SD_TC_DBG): 1 = skip the spike stores, 2 = skip the TMEM loads
   TcConfig c;
 };
-constexpr int kTraceStride = 64;   // int64 slots per CTA: [0] entry, [1] set-up done, [2] exit, then 8 per tile pass
+[[maybe_unused]] constexpr int kTraceStride = 64;   // int64 slots per CTA: [0] entry, [1] set-up done, [2] exit, then 8 per tile pass
 
 // ---------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -279,7 +279,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
-  long long* trace = p.trace ? p.trace + (int64_t)blockIdx.x * kTraceStride : nullptr;
+  // cycle-stamp diagnostics exist only in the -DSD_TRACE build (tools/trace_tc.py); the shipped kernel has none of it
+#ifdef SD_TRACE
+  long long* const trace = p.trace ? p.trace + (int64_t)blockIdx.x * kTraceStride : nullptr;
+  const int dbg = p.dbg;
+#else
+  constexpr long long* trace = nullptr;
+  constexpr int dbg = 0;
+#endif
   if (trace && threadIdx.x == 0) trace[0] = clock64();
 
   if (threadIdx.x == 0) {
@@ -463,7 +470,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
                   const uint64_t adesc = ((uint64_t)desc_hi << 32) | (a_lo + ks * a_step_k);
                   const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (b_lo0 + sp * b_step_sp + ks * b_step_k);
                   if (PAIR) tc_mma_f16_masked_pair(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first, km);
-                  else if (p.dbg & 4) tc_mma_f16(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first);   // timing experiment
+                  else if (dbg & 4) tc_mma_f16(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first);   // timing experiment
                   else tc_mma_f16_masked(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first, km[0], km[1], km[2], km[3]);
                 }
               }
@@ -606,7 +613,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
               packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&s2);
               if (want_sum) cnt2[j >> 1] = __hadd2(cnt2[j >> 1], s2);
             }
-            if (valid && n < p.Cout && p.out_spk != nullptr && !(p.dbg & 1)) {
+            if (valid && n < p.Cout && p.out_spk != nullptr && !(dbg & 1)) {
               const int t = tch * c.T_acc + tl;
               __half* o = p.out_spk + (((int64_t)t * p.Cout8 + (n >> 3)) * p.R_alloc + p.G + r) * 8;
               *reinterpret_cast<uint4*>(o) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -616,7 +623,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
           // two register sets: the TMEM load of timestep t + 1 is in flight while timestep t is computed
           auto lif_all = [&](auto fast_tag) {
             uint32_t accA[16], accB[16];
-            const bool ld = !(p.dbg & 2);
+            const bool ld = !(dbg & 2);
 #pragma unroll
             for (int j = 0; j < 16; ++j) accA[j] = accB[j] = 0u;
             if (ld) tc_ld16(t_base + (uint32_t)cc, accA);
@@ -755,20 +762,47 @@ __global__ void __launch_bounds__(256) lif_from_currents_kernel(const TcParams p
 // ---------------------------------------------------------------------------------------------------
 // Configuration (shared by weight packing and launch)
 // ---------------------------------------------------------------------------------------------------
-// Experiment knobs (SD_TC_*) are read from the environment on every call: they are only consulted while a plan is
-// being built (weight packing) and at launch, where they must agree, and getenv is ~100 ns.  Defaults are the measured
-// best (profiles/r01_experiments.md); none of them changes results except through fp32 summation order (KBLK):
+// Experiment knobs (SD_TC_*): read from the environment ONCE per process (first plan build); sd_debug_tc_reload_knobs
+// re-reads them for the sweep tool (tools/bench_layers.py).  Defaults are the measured best
+// (profiles/r01_experiments.md); none of them changes results except through fp32 summation order (KBLK):
 //   SD_TC_PAIR=0            single-CTA kernel instead of 2-CTA pairs
 //   SD_TC_SMALL_BATCH_SPLIT=0  keep N = 128 for a lone small batch
 //   SD_TC_TCHUNK=0 / SD_TC_TACC=n   one pass over all T / n timesteps per pass (n = 2: two TMEM stages)
 //   SD_TC_N256, SD_TC_WIDE256       N = 256 tiles with 2 timesteps per pass
 //   SD_TC_NTILE, SD_TC_KBLK, SD_TC_ACC_STAGES, SD_TC_ALIGN   tile shape overrides
 //   SD_TC_PERSIST=0         one work unit per CTA / cluster
-//   SD_TC_DBG (with sd_debug_tc_trace)   1: skip spike stores, 2: skip TMEM loads, 4: un-masked MMAs in the single-CTA
-//                           kernel (timing experiments only; 4 gives wrong results at image borders)
-static int env_int(const char* name, int dflt) {
-  const char* s = getenv(name);
-  return s ? atoi(s) : dflt;
+//   SD_TC_TPAR=0            no T-parallel small-batch mode
+//   SD_TC_DBG (-DSD_TRACE build only, with sd_debug_tc_trace)   1: skip spike stores, 2: skip TMEM loads, 4: un-masked
+//                           MMAs in the single-CTA kernel (timing experiments only; 4 gives wrong results at borders)
+struct TcKnobs {
+  int pair, small_batch_split, tchunk, tacc, wide256, n256, ntile, kblk, acc_stages, align, persist, tpar, dbg;
+};
+static TcKnobs g_knobs;
+static std::once_flag g_knobs_once;
+static void load_knobs() {
+  auto env_int = [](const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : dflt;
+  };
+  TcKnobs k;
+  k.pair = env_int("SD_TC_PAIR", 1);
+  k.small_batch_split = env_int("SD_TC_SMALL_BATCH_SPLIT", 1);
+  k.tchunk = env_int("SD_TC_TCHUNK", 1);
+  k.tacc = env_int("SD_TC_TACC", 0);
+  k.wide256 = env_int("SD_TC_WIDE256", 0);
+  k.n256 = env_int("SD_TC_N256", 0);
+  k.ntile = env_int("SD_TC_NTILE", 0);
+  k.kblk = env_int("SD_TC_KBLK", 0);
+  k.acc_stages = env_int("SD_TC_ACC_STAGES", -1);
+  k.align = env_int("SD_TC_ALIGN", 0);
+  k.persist = env_int("SD_TC_PERSIST", 1);
+  k.tpar = env_int("SD_TC_TPAR", 1);
+  k.dbg = env_int("SD_TC_DBG", 0);
+  g_knobs = k;
+}
+static const TcKnobs& knobs() {
+  std::call_once(g_knobs_once, load_knobs);
+  return g_knobs;
 }
 
 static int tc_supported(const sd_conv_desc* d, const char** why) {
@@ -791,16 +825,16 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
   const char* why;
   if (!tc_supported(d, &why)) { set_error("conv_tc: unsupported descriptor: %s", why); return SD_ERR_UNSUPPORTED; }
   c->T_acc = d->out_kind == SD_OUT_LIF ? d->T : 1;
-  if (d->out_kind == SD_OUT_LIF && d->T > 4 && d->T % 4 == 0 && env_int("SD_TC_TCHUNK", 1)) c->T_acc = 4;
+  if (d->out_kind == SD_OUT_LIF && d->T > 4 && d->T % 4 == 0 && knobs().tchunk) c->T_acc = 4;
   if (d->out_kind == SD_OUT_LIF) {
-    const int tacc = env_int("SD_TC_TACC", 0);           // experiment knob: timesteps per pass
+    const int tacc = knobs().tacc;           // experiment knob: timesteps per pass
     if (tacc > 0 && tacc <= d->T && d->T % tacc == 0) c->T_acc = tacc;
   }
   // Layers with exactly 256 output channels have only two N = 128 tiles per M tile, which quantises badly on 148 SMs
   // (98 M tiles -> 196 tiles -> 2 waves, the second one a third full).  One N = 256 tile per M tile with 2 timesteps
   // per pass does the same work in a single wave and fetches the A operand half as often per output column.
   bool wide = false;
-  if (d->out_kind == SD_OUT_LIF && d->C_out == 256 && d->T % 2 == 0 && d->T <= 4 && env_int("SD_TC_WIDE256", 0)) {
+  if (d->out_kind == SD_OUT_LIF && d->C_out == 256 && d->T % 2 == 0 && d->T <= 4 && knobs().wide256) {
     c->T_acc = 2;
     wide = true;
   }
@@ -808,7 +842,7 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
   int n_tile;
   // Larger N amortises the A-operand fetch from shared memory (4 KB per MMA whatever N is): measured on B200,
   // N = 128 without epilogue overlap beats N = 64 with two TMEM stages (profiles/).
-  if (c->T_acc * 256 <= 512 && d->C_out >= 256 && (wide || env_int("SD_TC_N256", 0))) n_tile = 256;
+  if (c->T_acc * 256 <= 512 && d->C_out >= 256 && (wide || knobs().n256)) n_tile = 256;
   else if (c->T_acc * 128 <= 512) n_tile = 128;
   else if (c->T_acc * 64 <= 512) n_tile = 64;
   else n_tile = 32;
@@ -823,8 +857,8 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
     // Only when the tiles cannot be paired (a single M tile): the cycle-stamp trace shows that an un-paired MMA costs
     // 72-79 cycles whatever N is (reading the 4 KB A operand from shared memory bounds it) while a paired N = 128 MMA does 8x the
     // work of an N = 32 one in 64 cycles, and the K loop per CTA - the critical path of a small batch - is the same.
-    const bool can_pair = env_int("SD_TC_PAIR", 1) && m_tiles >= 2 && n_tile == 128;
-    while (n_tile > 32 && env_int("SD_TC_SMALL_BATCH_SPLIT", 1) && !can_pair &&
+    const bool can_pair = knobs().pair && m_tiles >= 2 && n_tile == 128;
+    while (n_tile > 32 && knobs().small_batch_split && !can_pair &&
            (int64_t)m_tiles * ((d->C_out + n_tile - 1) / n_tile) * 2 * conc <= sms && d->C_out > n_tile / 2)
       n_tile /= 2;
   }
@@ -832,7 +866,7 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
   // half of the clusters runs its passes as independent work units (x T/4 parallelism at full tile efficiency) and
   // leaves the LIF recurrence to a second kernel.  The per-CTA K loop, which bounds a small batch, gets T/4 x shorter.
   c->tpar = 0;
-  if (d->out_kind == SD_OUT_LIF && c->n_tchunks > 1 && d->concurrent <= 1 && env_int("SD_TC_TPAR", 1)) {
+  if (d->out_kind == SD_OUT_LIF && c->n_tchunks > 1 && d->concurrent <= 1 && knobs().tpar) {
     check_device();
     const int sms = sm_count() > 0 ? sm_count() : 148;
     const int64_t rows = (int64_t)d->B * d->H_in * d->W_in;
@@ -843,7 +877,7 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
       n_tile = 128;
     }
   }
-  n_tile = env_int("SD_TC_NTILE", n_tile);
+  if (knobs().ntile > 0) n_tile = knobs().ntile;
   while (n_tile > 32 && n_tile / 2 >= d->C_out) n_tile /= 2;
   if (!(n_tile == 32 || n_tile == 64 || n_tile == 128 || n_tile == 256) || c->T_acc * n_tile > 512) {
     set_error("conv_tc: bad N tile %d for T=%d", n_tile, c->T_acc);
@@ -853,16 +887,16 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
   {
     const int64_t rows = (int64_t)d->B * d->H_in * d->W_in;
     const int m_tiles = (int)((rows + kTileRows - 1) / kTileRows);
-    c->pair = (env_int("SD_TC_PAIR", 1) && n_tile == 128 && m_tiles >= 2) ? 1 : 0;
+    c->pair = (knobs().pair && n_tile == 128 && m_tiles >= 2) ? 1 : 0;
   }
   c->acc_stages = 512 / (c->T_acc * n_tile) >= 2 ? 2 : 1;
-  c->acc_stages = env_int("SD_TC_ACC_STAGES", c->acc_stages) >= 2 && 512 / (c->T_acc * n_tile) >= 2 ? 2 : 1;
+  if (knobs().acc_stages >= 0) c->acc_stages = knobs().acc_stages >= 2 && 512 / (c->T_acc * n_tile) >= 2 ? 2 : 1;
   const int c0 = d->C_in0, c1 = d->C_in - d->C_in0;
   const int Wp = d->W_in;   // row stride of the dense pixel grid
   // Measured on B200 (profiles/r1_layer_sweep.txt): the pre-shifted (128-byte aligned) variant is SLOWER than plain
   // 16-byte-aligned tap starts (its 3x larger A stage forces KBLK = 16), so it is opt-in only.
-  const int want_align = env_int("SD_TC_ALIGN", 0);
-  const int kblk_pref = env_int("SD_TC_KBLK", 0);
+  const int want_align = knobs().align;
+  const int kblk_pref = knobs().kblk;
   bool found = false;
   for (int ndx = (want_align && Wp % 8 == 0) ? 3 : 1; ndx >= 1 && !found; ndx -= 2) {
     c->ndx = ndx;
@@ -963,7 +997,9 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, const int* __restric
 
 using namespace sd;
 
-static long long* g_tc_trace = nullptr;   // diagnostics only (tools/trace_tc.py); not thread-safe by design
+#ifdef SD_TRACE
+static long long* g_tc_trace = nullptr;   // diagnostics build only (tools/trace_tc.py); not thread-safe by design
+#endif
 
 extern "C" {
 
@@ -971,8 +1007,22 @@ extern "C" {
 // grid * 64 int64; pass null to switch tracing off).  Layout per CTA: [0] entry, [1] set-up done, [2] exit, then per
 // tile pass i < 7 at 3 + 8 i: MMA warp got the accumulator, first operands landed, last MMA issued, cycles the MMA warp
 // waited for operands, epilogue saw the accumulator, epilogue released it.
+// Only the -DSD_TRACE build of the library (tools/trace_tc.py builds it) carries the stamps; the shipped one refuses.
 int sd_debug_tc_trace(void* buf) {
+#ifdef SD_TRACE
   g_tc_trace = (long long*)buf;
+  return SD_OK;
+#else
+  if (buf == nullptr) return SD_OK;
+  set_error("sd_debug_tc_trace: this library was built without -DSD_TRACE (tools/trace_tc.py builds the diagnostics variant)");
+  return SD_ERR_UNSUPPORTED;
+#endif
+}
+
+// Diagnostics: re-read the SD_TC_* environment knobs (tools/bench_layers.py sweeps them inside one process).
+int sd_debug_tc_reload_knobs(void) {
+  knobs();
+  load_knobs();
   return SD_OK;
 }
 
@@ -1072,11 +1122,13 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
   // cute::UMMA::InstrDescriptor: c_format F32 (bit 4), a/b F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
   p.idesc = (1u << 4) | ((uint32_t)(c.N_TILE >> 3) << 17) | ((uint32_t)((c.pair ? 2 * kTileRows : kTileRows) >> 4) << 24);
   p.c = c;
+#ifdef SD_TRACE
   p.trace = g_tc_trace;
-  p.dbg = g_tc_trace ? env_int("SD_TC_DBG", 0) : 0;
+  p.dbg = g_tc_trace ? knobs().dbg : 0;
+#endif
   cudaStream_t st = as_stream(stream);
   int grid;
-  const bool persist = env_int("SD_TC_PERSIST", 1) != 0;   // experiment knob: 0 = one work unit per CTA / cluster
+  const bool persist = knobs().persist != 0;   // experiment knob: 0 = one work unit per CTA / cluster
   const int unit_mult = c.tpar ? c.n_tchunks : 1;
   if (c.pair) {
     const int units = ((c.m_tiles + 1) / 2) * c.n_tiles * unit_mult;
@@ -1087,13 +1139,15 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
   }
 #define SD_TC_LAUNCH_ONE(NS, KS, PR)                                                                               \
   do {                                                                                                             \
-    static std::once_flag once;                                                                                    \
-    static cudaError_t attr_rc = cudaSuccess;                                                                      \
-    std::call_once(once, [] {                                                                                      \
-      attr_rc = cudaFuncSetAttribute(conv3x3_tc_kernel<NS, KS, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                     227 * 1024);                                                                  \
+    /* the attribute belongs to the function in ONE device's context: set it once per device */                   \
+    static std::once_flag once[64];                                                                                \
+    static cudaError_t attr_rc[64];                                                                                \
+    const int dev_ = current_device_index();                                                                       \
+    std::call_once(once[dev_], [dev_] {                                                                            \
+      attr_rc[dev_] = cudaFuncSetAttribute(conv3x3_tc_kernel<NS, KS, PR>,                                          \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);               \
     });                                                                                                            \
-    SD_CUDA(attr_rc);                                                                                              \
+    SD_CUDA(attr_rc[dev_]);                                                                                        \
     cudaLaunchConfig_t cfg = {};                                                                                   \
     cfg.gridDim = dim3((unsigned)grid);                                                                            \
     cfg.blockDim = dim3(kTcThreads);                                                                               \

@@ -21,41 +21,54 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// Device facts are cached PER DEVICE (a process may drive several GPUs: the current device at call time decides).
 static std::mutex g_dev_mu;
-static int g_dev_state = -1;  // -1 unknown, 0 ok, else error code
-static int g_sm_count = 0, g_max_thr = 0, g_cc_major = 0, g_cc_minor = 0;
+constexpr int kMaxDevices = 64;
+struct DevInfo { int state = -1; int sm_count = 0, max_thr = 0, cc_major = 0, cc_minor = 0; };   // state: -1 unknown, 0 ok
+static DevInfo g_dev[kMaxDevices];
+static int g_no_device = -1;   // -1 unknown, 0 some device exists, else error code
+
+int current_device_index() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
 
 int check_device() {
   std::lock_guard<std::mutex> lk(g_dev_mu);
-  if (g_dev_state >= 0) {
-    if (g_dev_state != SD_OK) set_error("no sm_100 CUDA device available (libsd_b200 has no CPU fallback)");
-    return g_dev_state;
+  if (g_no_device < 0) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      g_no_device = SD_ERR_NO_DEVICE;
+      set_error("no CUDA device available (libsd_b200 has no CPU fallback): %s", cudaGetErrorString(e));
+      return g_no_device;
+    }
+    g_no_device = 0;
   }
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n == 0) {
-    cudaGetLastError();
-    g_dev_state = SD_ERR_NO_DEVICE;
-    set_error("no CUDA device available (libsd_b200 has no CPU fallback): %s", cudaGetErrorString(e));
-    return g_dev_state;
+  if (g_no_device != 0) {
+    set_error("no sm_100 CUDA device available (libsd_b200 has no CPU fallback)");
+    return g_no_device;
   }
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceProp p;
-  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess || p.major != 10) {
-    g_dev_state = SD_ERR_NO_DEVICE;
-    set_error("device is not compute capability 10.x (libsd_b200 is built for sm_100a only)");
-    return g_dev_state;
+  DevInfo& d = g_dev[current_device_index()];
+  if (d.state < 0) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, current_device_index()) != cudaSuccess || p.major != 10) {
+      d.state = SD_ERR_NO_DEVICE;
+    } else {
+      d.sm_count = p.multiProcessorCount;
+      d.max_thr = p.maxThreadsPerMultiProcessor;
+      d.cc_major = p.major;
+      d.cc_minor = p.minor;
+      d.state = SD_OK;
+    }
   }
-  g_sm_count = p.multiProcessorCount;
-  g_max_thr = p.maxThreadsPerMultiProcessor;
-  g_cc_major = p.major;
-  g_cc_minor = p.minor;
-  g_dev_state = SD_OK;
-  return SD_OK;
+  if (d.state != SD_OK) set_error("device is not compute capability 10.x (libsd_b200 is built for sm_100a only)");
+  return d.state;
 }
-int sm_count() { return g_sm_count; }
-int max_threads_per_sm() { return g_max_thr; }
+int sm_count() { return g_dev[current_device_index()].sm_count; }
+int max_threads_per_sm() { return g_dev[current_device_index()].max_thr; }
 
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ld_stream(const float4* p) {
@@ -338,10 +351,11 @@ int sd_version(void) { return 1; }
 
 int sd_device_info(int* sms, int* max_thr, int* cc_major, int* cc_minor) {
   SD_DEVICE_OR_RETURN();
-  if (sms) *sms = g_sm_count;
-  if (max_thr) *max_thr = g_max_thr;
-  if (cc_major) *cc_major = g_cc_major;
-  if (cc_minor) *cc_minor = g_cc_minor;
+  const DevInfo& d = g_dev[current_device_index()];
+  if (sms) *sms = d.sm_count;
+  if (max_thr) *max_thr = d.max_thr;
+  if (cc_major) *cc_major = d.cc_major;
+  if (cc_minor) *cc_minor = d.cc_minor;
   return SD_OK;
 }
 

@@ -26,12 +26,55 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
                            "(the CPU oracle lives under oracle/ and is test infrastructure only)")
 
 
+def module_cache_key(module: torch.nn.Module) -> tuple:
+    """Everything a cached plan of ``module`` depends on besides the shape: parameter and buffer versions (bumped by
+    optimizer steps, ``load_state_dict`` and other in-place tensor ops), the hyper-parameters that are baked into a
+    plan (LIF tau / threshold / reset value, BatchNorm eps) and the device.  NOT covered: in-place edits through
+    ``.data`` (``p.data.copy_()``, EMA swaps), which do not bump ``_version`` -- call ``invalidate_plans()`` after
+    those."""
+    hyper = []
+    for m in module.modules():
+        if hasattr(m, "v_threshold") and hasattr(m, "tau"):
+            hyper.append((float(m.tau), float(m.v_threshold), None if m.v_reset is None else float(m.v_reset),
+                          bool(getattr(m, "decay_input", True))))
+        elif isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            hyper.append((float(m.eps),))
+    dev = _lib.first_cuda_device(module)
+    return (tuple(p._version for p in module.parameters()), tuple(b._version for b in module.buffers()),
+            tuple(hyper), dev)
+
+
+class PlanCacheMixin:
+    """For nn.Modules that cache fused plans in ``self._plans``: explicit invalidation, and plans (ctypes function
+    pointers, CUDA streams and graphs, device buffers) are kept out of pickling / copy.deepcopy / torch.save(module)."""
+
+    def invalidate_plans(self) -> None:
+        self._plans = {}
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_plans"] = {}
+        return state
+
+
+def _coef_array(coef: torch.Tensor, T: int):
+    """The T memout coefficients as a host float array.  A coefficient buffer bound to another T (SURVEY.md finding 1:
+    checkpoints carry ``memout.coef`` of shape (16,1,1,1,1)) raises the broadcasting RuntimeError the reference raises
+    at R/snn_model/snn_layers.py:38 -- the fused plans must not silently truncate or zero-pad it."""
+    c = coef.detach().reshape(-1).cpu().tolist()
+    if len(c) != T:
+        raise RuntimeError(f"The size of tensor a ({T}) must match the size of tensor b ({len(c)}) at "
+                           "non-singleton dimension 0")
+    return (ctypes.c_float * T)(*[float(v) for v in c])
+
+
 def stf_empty(T: int, B: int, C: int, H: int, W: int, device) -> torch.Tensor:
     """Zero-filled STF buffer (pad/guard rows must stay zero; kernels only write valid rows)."""
     n = lib().sd_stf_bytes(T, B, C, H, W) // 2
     return torch.zeros(n, dtype=torch.float16, device=device)
 
 
+@_lib.on_device_of
 def stf_from_nchw(x: torch.Tensor) -> torch.Tensor:
     T, B, C, H, W = x.shape
     out = torch.empty(lib().sd_stf_bytes(T, B, C, H, W) // 2, dtype=torch.float16, device=x.device)
@@ -39,6 +82,7 @@ def stf_from_nchw(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_lib.on_device_of
 def stf_to_nchw(stf: torch.Tensor, T: int, B: int, C: int, H: int, W: int) -> torch.Tensor:
     out = torch.empty((T, B, C, H, W), dtype=torch.float32, device=stf.device)
     check(lib().sd_stf_to_nchw(ptr(stf), ptr(out), T, B, C, H, W, stream_ptr()))
@@ -142,7 +186,7 @@ class FusedLayer:
         if out_kind == _lib.OUT_MEMOUT_TANH:
             if memout_coef is None:
                 raise ValueError("memout_coef required for the memout+tanh tail")
-            self._coef = (ctypes.c_float * T)(*[float(v) for v in memout_coef.detach().reshape(-1).cpu().tolist()[:T]])
+            self._coef = _coef_array(memout_coef, T)
 
     def flops(self) -> int:
         """Dense algorithmic FLOPs (2*MAC) of one call, counted as SURVEY.md section 8(d) does."""
@@ -219,6 +263,11 @@ class DenoiserPlan:
     def flops(self) -> int:
         return sum(l.flops() for l in self.layers)
 
+    def spikes_nchw(self, buf: torch.Tensor, lyr: "FusedLayer") -> torch.Tensor:
+        """The spikes a fused layer left in its inter-layer buffer, as the reference's fp32 [T, b, C, h, w] tensor
+        (diagnostics / parity tests; the product path never converts)."""
+        return stf_to_nchw(buf, lyr.T, lyr.B, lyr.C_out, lyr.H_out, lyr.W_out)
+
     def run_from_input(self) -> torch.Tensor:
         self.l1.run(self.xin, self.x1, out_sum=self.x1s)
         self.l2.run(self.x1, self.x2)
@@ -240,11 +289,23 @@ class DenoiserPlan:
         return self.run_from_input()
 
 
+def cluster_count() -> int:
+    """2-SM clusters of the current device (sm_count / 2: 74 on a B200); 74 when no device is present (host-side
+    planning tests run without a GPU)."""
+    sms = ctypes.c_int(0)
+    try:
+        if lib().sd_device_info(ctypes.byref(sms), None, None, None) == 0 and sms.value > 0:
+            return sms.value // 2
+    except Exception:  # noqa: BLE001  (library not built: the caller fails loudly at its first kernel call)
+        pass
+    return 74
+
+
 def plan_sub_batches(b: int, rows_per_image: int, n_streams: Optional[int] = None) -> list:
     """Sizes of the concurrent sub-batches of a shard of ``b`` images (measured on B200, profiles/r01_experiments.md).
 
     The tcgen05 layers work on pairs of 128-row tiles (256 rows of the dense b*h*w pixel grid), one pair per 2-SM
-    cluster, 74 clusters:
+    cluster, sm_count / 2 = 74 clusters on a B200:
      * a shard of at most one wave of pairs runs best as up to 5 concurrent sub-batches of >= 5 pairs (their layers
        pack the SMs like small items pack a bin); larger shards as 2 (fewer, longer launches; the GPU is power-capped
        there); below 64 images sub-batches would only add launches;
@@ -253,7 +314,7 @@ def plan_sub_batches(b: int, rows_per_image: int, n_streams: Optional[int] = Non
     total_pairs = -(-b * rows_per_image // 256)
     if n_streams is None:
         env = os.environ.get("SD_SAMPLER_STREAMS")
-        n_streams = int(env) if env else (min(5, max(1, total_pairs // 5)) if total_pairs <= 74 else 2)
+        n_streams = int(env) if env else (min(5, max(1, total_pairs // 5)) if total_pairs <= cluster_count() else 2)
     if b < 64:
         n_streams = 1
     n_streams = max(1, min(n_streams, b))
@@ -294,6 +355,7 @@ class SamplerPlan:
         self.n_tokens_global = (n_global if n_global is not None else b) * hw
         self.token_base = shard_base * hw
         dev = model.conv1[0].weight.device
+        self.device = dev
         self.x_t = torch.empty(self.n_tokens, dtype=torch.int64, device=dev)
         self.unmasked = torch.empty(self.n_tokens, dtype=torch.uint8, device=dev)
         self.subs = []
@@ -319,7 +381,7 @@ class SamplerPlan:
     def offset_advance(self, sample_steps: int) -> int:
         return sample_steps * (self.inc_u + self.inc_e)
 
-    def _step(self, dp, lo, bi, t, temp, seed, off, rng_dev=None):
+    def _step(self, dp, lo, bi, t, temp, seed, off, rng_dev=None, hist_row=None):
         hw = self.h * self.w
         xs = self.x_t[lo * hw:(lo + bi) * hw]
         us = self.unmasked[lo * hw:(lo + bi) * hw]
@@ -332,8 +394,10 @@ class SamplerPlan:
             check(lib().sd_sample_step_dev(ptr(logits), ptr(xs), ptr(us), None, bi * hw, self.K, t, float(temp),
                                            ptr(rng_dev), off, off + self.inc_u, self.token_base + lo * hw,
                                            self.n_tokens_global, stream_ptr()))
+        if hist_row is not None:   # parity diagnostics: the token grid after this step (tests/test_gpu_sample_parity.py)
+            hist_row[lo * hw:(lo + bi) * hw].copy_(xs)
 
-    def _enqueue(self, temp, sample_steps, seed, offset0, fill_x, fill_u, rng_dev=None):
+    def _enqueue(self, temp, sample_steps, seed, offset0, fill_x, fill_u, rng_dev=None, history=None):
         """Enqueue the whole reverse-diffusion loop on the current stream (+ the sub-batch streams)."""
         if fill_x:
             self.x_t.fill_(self.mask_id)
@@ -348,12 +412,13 @@ class SamplerPlan:
                 s.wait_event(start)
         off = int(offset0)
         for t in range(sample_steps, 0, -1):
+            row = None if history is None else history[sample_steps - t]
             for (dp, lo, bi), s in zip(self.subs, self.streams):
                 if multi:
                     with torch.cuda.stream(s):
-                        self._step(dp, lo, bi, t, temp, seed, off, rng_dev)
+                        self._step(dp, lo, bi, t, temp, seed, off, rng_dev, row)
                 else:
-                    self._step(dp, lo, bi, t, temp, seed, off, rng_dev)
+                    self._step(dp, lo, bi, t, temp, seed, off, rng_dev, row)
             off += self.inc_u + self.inc_e
         if multi:
             for s in self.streams:
@@ -363,7 +428,7 @@ class SamplerPlan:
 
     def sample(self, temp: float, sample_steps: int, seed: int, offset0: int = 0,
                x_init: Optional[torch.Tensor] = None, unmasked_init: Optional[torch.Tensor] = None,
-               use_graph: Optional[bool] = None) -> torch.Tensor:
+               use_graph: Optional[bool] = None, history: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x_init / unmasked_init (host or device, [b,1,h,w] or flat): start from a partially unmasked grid
         instead of the all-mask grid of vq_diffusion.py:106-107; copied on the current stream (pinned host -> device).
 
@@ -377,8 +442,13 @@ class SamplerPlan:
             self.x_t.copy_(x_init.reshape(-1), non_blocking=True)
         if unmasked_init is not None:
             self.unmasked.copy_(unmasked_init.reshape(-1), non_blocking=True)
+        if history is not None:
+            # int64 [sample_steps, b*h*w] device buffer receiving the token grid after every step (diagnostics; eager)
+            if history.shape != (sample_steps, self.n_tokens) or history.dtype != torch.int64 or not history.is_cuda:
+                raise ValueError(f"history must be a CUDA int64 tensor of shape ({sample_steps}, {self.n_tokens})")
+            use_graph = False
         if not use_graph:
-            self._enqueue(temp, sample_steps, seed, offset0, x_init is None, unmasked_init is None)
+            self._enqueue(temp, sample_steps, seed, offset0, x_init is None, unmasked_init is None, history=history)
             return self.x_t.view(self.b, 1, self.h, self.w)
         if not hasattr(self, "rng_dev"):
             self.rng_dev = torch.zeros(2, dtype=torch.int64, device=self.x_t.device)
@@ -504,7 +574,7 @@ class VQVAEPlan:
         self.recon = self.d3.alloc_out()
         self._vq = vq
         self._states, self._captured = None, None
-        self._coef_vq = (ctypes.c_float * T)(*vq.memout.coef.detach().reshape(-1).cpu().tolist()[:T])
+        self._coef_vq = _coef_array(vq.memout.coef, T)
 
     def _state(self, name: str, lyr: "FusedLayer") -> Optional[torch.Tensor]:
         """Fresh LIF state buffer (planar layout, reset value) for layer ``name`` while states are being captured."""
@@ -598,6 +668,7 @@ class VQVAEPlan:
         return sum(l.flops() for l in (self.e1, self.e2, self.e3, self.gen, self.d1, self.d2, self.d3))
 
 
+@_lib.on_device_of
 def to_uint8(pred: torch.Tensor) -> torch.Tensor:
     out = torch.empty(pred.shape, dtype=torch.uint8, device=pred.device)
     check(lib().sd_to_uint8(ptr(pred.contiguous()), ptr(out), pred.numel(), stream_ptr()))

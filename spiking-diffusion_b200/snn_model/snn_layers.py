@@ -9,7 +9,7 @@ import ctypes
 import torch
 import torch.nn as nn
 
-from .._lib import check, lib, ptr, stream_ptr
+from .._lib import check, lib, on_device_of, ptr, stream_ptr
 
 
 class MembraneOutputLayer(nn.Module):
@@ -26,6 +26,7 @@ class MembraneOutputLayer(nn.Module):
                                "non-singleton dimension 0")
         return (ctypes.c_float * T)(*c)
 
+    @on_device_of
     def forward(self, x: torch.Tensor, apply_tanh: bool = False) -> torch.Tensor:
         """x: (T, N, C, H, W) -> sum_t coef[t] * x[t]."""
         if not x.is_cuda:

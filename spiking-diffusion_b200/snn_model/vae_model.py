@@ -17,7 +17,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib, engine
-from .._lib import check, lib, ptr, stream_ptr
+from .._lib import check, lib, on_device_of, ptr, stream_ptr
 from ..activation_based import base, layer, neuron, surrogate
 from .snn_layers import PSP, MembraneOutputLayer
 
@@ -45,6 +45,7 @@ class VectorQuantizer(nn.Module):
             neuron.LIFNode(surrogate_function=surrogate.ATan()),
         )
 
+    @on_device_of
     def feature(self, x: torch.Tensor) -> torch.Tensor:
         """(1-alpha)*memout(x) + alpha*sum_t x/T as fp32 [N, h, w, D]   (vae_model.py:42-44)."""
         T, N, D, h, w = x.shape
@@ -54,6 +55,7 @@ class VectorQuantizer(nn.Module):
                                   ptr(z), T, N, D, h, w, stream_ptr()))
         return z
 
+    @on_device_of
     def forward(self, x: torch.Tensor):
         """x: [T, N, D, h, w] spikes.  eval -> (spikes [T,N,D,h,w], indices [N*h*w] int64)  (vae_model.py:53-58);
         train -> (spikes, loss_1 + loss_2)  (vae_model.py:61-85)."""
@@ -91,14 +93,26 @@ class VectorQuantizer(nn.Module):
         loss_2 = q_latent_loss_2 + self.commitment_cost * e_latent_loss_2
         return quantized, loss_1 + loss_2
 
+    @on_device_of
     def forward_with_loss(self, x: torch.Tensor):
-        """(quantized, loss, indices): eval-mode loss is the VQ objective value, for monitoring only."""
+        """(quantized, loss, indices) -- the 3-tuple named in BASELINE.json:north_star.
+        train: the reference's training branch (vae_model.py:61-85), loss = loss_1 + loss_2 with gradients, indices
+        from get_code_indices on the same feature; eval: the VQ objective value (no PSP term), for monitoring only."""
+        if self.training:
+            quantized, loss = self._forward_train(x)
+            with torch.no_grad():
+                T = x.shape[0]
+                x_memout = (1 - self.alpha) * self.memout(x) + self.alpha * torch.sum(x, dim=0) / T
+                flat = x_memout.permute(0, 2, 3, 1).reshape(-1, self.embedding_dim)
+                idx = self.get_code_indices(flat)
+            return quantized, loss, idx
         quantized, idx = self.forward(x)
         x_memout = self.feature(x)
         q = self.quantize(idx).view_as(x_memout)
         mse = torch.mean((q - x_memout) ** 2)
         return quantized, mse + self.commitment_cost * mse, idx
 
+    @on_device_of
     def get_code_indices(self, flat_x: torch.Tensor) -> torch.Tensor:
         """argmin_k |z|^2 + |e_k|^2 - 2 z.e_k, first index on ties  (vae_model.py:87-95)."""
         if not flat_x.is_cuda:
@@ -109,6 +123,7 @@ class VectorQuantizer(nn.Module):
                                  self.embedding_dim, self.num_embeddings, stream_ptr()))
         return idx
 
+    @on_device_of
     def quantize(self, encoding_indices: torch.Tensor) -> torch.Tensor:
         """Embedding rows for a tensor of indices: [...] -> [..., D]  (vae_model.py:97-99; called directly by
         R/main.py:264,389,424 with indices of shape [b, 7, 7])."""
@@ -173,7 +188,7 @@ class Decoder(nn.Module):
         return self.snn_convs(x)  # [t, b, c, h, w]
 
 
-class SNN_VQVAE(nn.Module):
+class SNN_VQVAE(engine.PlanCacheMixin, nn.Module):
     """VQ-SVAE (vae_model.py:161-196)."""
 
     def __init__(self, in_dim, embedding_dim, num_embeddings, data_variance, commitment_cost=0.25, T: int = 16):
@@ -191,12 +206,12 @@ class SNN_VQVAE(nn.Module):
 
     def plan(self, T: int, B: int, H: int, W: int) -> "engine.VQVAEPlan":
         """Fully fused plan for a fixed shape (no fp32 round trips between stages; used by sampling/decoding)."""
-        key = (T, B, H, W, tuple(p._version for p in self.parameters()), tuple(b._version for b in self.buffers()),
-               next(self.parameters()).device)
+        key = (T, B, H, W) + engine.module_cache_key(self)
         if self._plans.get("key") != key:
             self._plans = {"key": key, "plan": engine.VQVAEPlan(self, T, B, H, W)}
         return self._plans["plan"]
 
+    @on_device_of
     def forward(self, x, image):
         """x: [T, B, C, H, W].  eval -> (e, x_recon, encoding_indices)   (vae_model.py:181-187);
         train -> (e_q_loss, recon_loss, real_recon_loss)                   (vae_model.py:189-196)."""
@@ -237,6 +252,7 @@ class SNN_VQVAE(nn.Module):
         e = engine.stf_to_nchw(e_stf, T, B, self.embedding_dim, plan.h, plan.w)
         return e, rec.clone(), idx.clone()
 
+    @on_device_of
     @torch.no_grad()
     def decode_indices(self, sample: torch.Tensor, T: int = None) -> torch.Tensor:
         """The caller-side decode of R/main.py:388-399 as one fused chain:

@@ -16,7 +16,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib, engine
-from .._lib import check, lib, ptr, stream_ptr
+from .._lib import check, lib, on_device_of, ptr, stream_ptr
+from ..activation_based import base
 from ..activation_based import functional, layer, neuron, surrogate
 
 
@@ -55,7 +56,7 @@ def load_reference_state_dict(module, state_dict, strict: bool = True):
     return module.load_state_dict(fixed, strict=strict)
 
 
-class DummyModel(nn.Module):
+class DummyModel(engine.PlanCacheMixin, nn.Module):
     """6-layer spiking conv denoiser with one skip connection (vq_diffusion.py:150-208)."""
 
     def __init__(self, n_channel: int, num_embeddings, T: int = 16) -> None:
@@ -77,18 +78,19 @@ class DummyModel(nn.Module):
         self.nsplit = 2   # fp16 terms per fp32 weight in the tcgen05 layers (2 = 22-bit weights, 1 = 11-bit)
 
     def plan(self, b: int, h: int, w: int) -> "engine.DenoiserPlan":
-        key = (self.T, b, h, w, self.nsplit, tuple(p._version for p in self.parameters()),
-               tuple(bf._version for bf in self.buffers()), next(self.parameters()).device)
+        key = (self.T, b, h, w, self.nsplit) + engine.module_cache_key(self)
         if self._plans.get("key") != key:
             self._plans = {"key": key, "plan": engine.DenoiserPlan(self, self.T, b, h, w, nsplit=self.nsplit)}
         return self._plans["plan"]
 
+    @on_device_of
     def forward(self, x, t) -> torch.Tensor:
         """x: [b, 1, h, w] float token ids, t: [b] long -> logits [b, K, h, w]  (vq_diffusion.py:189-208).
 
         The whole network runs as one fused chain, so the per-layer LIF states are consumed inside the kernels:
         this equals the reference whenever the net is reset between calls, which every reference call site does
-        (vq_diffusion.py:129, R/main.py:249,391)."""
+        (vq_diffusion.py:129, R/main.py:249,391).  A second forward WITHOUT a reset would continue from the carried
+        state in the reference; here it raises (the nodes are marked ``base.ConsumedState`` until reset)."""
         if not x.is_cuda:
             raise RuntimeError("DummyModel.forward needs CUDA tensors: there is no CPU path")
         if self.training:
@@ -99,11 +101,14 @@ class DummyModel(nn.Module):
             x5 = self.conv5(self.conv4(self.conv3(self.conv2(x1))))
             x6 = self.conv6(torch.cat((x5, x1), dim=2))
             return torch.sum(x6, dim=0) / self.T
-        for m in self.modules():
-            if isinstance(m, neuron.LIFNode) and isinstance(m.v, torch.Tensor):
+        nodes = [(n, m) for n, m in self.named_modules() if isinstance(m, neuron.LIFNode)]
+        for _, m in nodes:
+            if not m.memory_is_reset("v"):
                 raise RuntimeError("DummyModel.forward starts from reset LIF state; call functional.reset_net(model) first")
         b, _, h, w = x.shape
         logits = self.plan(b, h, w).run(x.float(), t)
+        for n, m in nodes:
+            m.v = base.ConsumedState(f"DummyModel.{n}")
         return logits.permute(0, 3, 1, 2).contiguous()
 
 
@@ -112,7 +117,7 @@ class Sampler(nn.Module):
         super().__init__()
 
 
-class AbsorbingDiffusion(Sampler):
+class AbsorbingDiffusion(engine.PlanCacheMixin, Sampler):
     def __init__(self, denoise_fn, mask_id, shape=(7, 7), n_samples: int = 16):
         super().__init__()
         self.num_classes = denoise_fn.num_embeddings
@@ -162,28 +167,30 @@ class AbsorbingDiffusion(Sampler):
             raise ValueError
         return loss.mean()
 
+    @on_device_of
     def train_iter(self, x):
         return {"loss": self._train_loss(x)}
 
     def plan(self, b: int, n_global=None, shard_base: int = 0) -> "engine.SamplerPlan":
         h, w = self.shape
         m = self._denoise_fn
-        key = (b, h, w, m.T, m.nsplit, int(self.mask_id), n_global, shard_base,
-               tuple(p._version for p in m.parameters()), tuple(bf._version for bf in m.buffers()),
-               next(m.parameters()).device)
+        key = (b, h, w, m.T, m.nsplit, int(self.mask_id), n_global, shard_base) + engine.module_cache_key(m)
         if self._plans.get("key") != key:
             self._plans = {"key": key, "plan": engine.SamplerPlan(m, m.T, b, h, w, int(self.mask_id), n_global,
                                                                   shard_base, nsplit=m.nsplit)}
         return self._plans["plan"]
 
+    @on_device_of
     @torch.no_grad()
     def sample(self, temp=1.0, sample_steps=None, seed=None, offset=0, n_global=None, shard_base: int = 0,
-               x_init=None, unmasked_init=None):
+               x_init=None, unmasked_init=None, history=None):
         """Reverse process (vq_diffusion.py:103-142) -> x_t int64 [b, 1, h, w] with no mask tokens left.
 
         ``n_global`` / ``shard_base``: this call generates images [shard_base, shard_base + n_samples) of a global
         batch of ``n_global``; each shard evaluates the Philox values of its global element indices, so sharding the
-        batch over GPUs reproduces the single-GPU stream (no collective on this path)."""
+        batch over GPUs reproduces the single-GPU stream (no collective on this path).
+        ``history``: optional CUDA int64 [sample_steps, b*h*w] buffer that receives the token grid after every step
+        (parity diagnostics; the loop then runs eagerly instead of as a CUDA graph)."""
         if self._denoise_fn.training:
             raise NotImplementedError("sample() runs the denoiser in eval mode; call denoise_fn.eval()")
         b = int(self.n_samples)
@@ -194,6 +201,7 @@ class AbsorbingDiffusion(Sampler):
             gen = torch.cuda.default_generators[torch.cuda.current_device()]
             seed, offset = gen.initial_seed(), gen.get_offset()
             gen.set_offset(offset + plan.offset_advance(sample_steps))
-        x_t = plan.sample(float(temp), int(sample_steps), int(seed), int(offset), x_init, unmasked_init)
+        x_t = plan.sample(float(temp), int(sample_steps), int(seed), int(offset), x_init, unmasked_init,
+                          history=history)
         functional.reset_net(self._denoise_fn)
         return x_t.clone()

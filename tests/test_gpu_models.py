@@ -241,3 +241,69 @@ def test_fused_eval_forward_keeps_the_lif_state_protocol():
     assert float((idx2 != idx_ref2).float().mean()) <= 0.02
     functional.reset_net(m)
     assert m._all_lif_reset()
+
+
+# ---- round 2: ADVICE.md behaviours on the device ---------------------------------------------------------------------
+def test_fused_path_rejects_input_T_that_differs_from_the_models_T():
+    """SNN_VQVAE(T=16) fed a T=4 sequence: the module-by-module path and the reference raise a broadcasting
+    RuntimeError at the memout coefficients (SURVEY.md finding 1); the fused plan must raise the same, not silently
+    use 0.8^15..0.8^12."""
+    m, _ = make_vqvae(16, 128, seed=0)
+    img = synth.synth_images(0, 2).cuda()
+    xs4 = img.unsqueeze(0).repeat(4, 1, 1, 1, 1)
+    with pytest.raises(RuntimeError, match="must match the size of tensor b"):
+        m(xs4, img)
+    functional.reset_net(m)
+    with pytest.raises(RuntimeError, match="must match the size of tensor b"):
+        m.decode_indices(torch.zeros((2, 7, 7), dtype=torch.int64, device="cuda"), T=4)
+    functional.reset_net(m)
+    e, rec, idx = m(img.unsqueeze(0).repeat(16, 1, 1, 1, 1), img)        # the model's own T still works
+    assert rec.shape == (2, 1, 28, 28)
+    functional.reset_net(m)
+
+
+def test_denoiser_second_eval_forward_without_reset_raises():
+    den, _ = make_denoiser(4, 128, seed=0)
+    x = torch.full((2, 1, 7, 7), 128.0, device="cuda")
+    t = torch.full((2,), 7, device="cuda", dtype=torch.long)
+    a = den(x, t)
+    with pytest.raises(RuntimeError, match="reset_net"):
+        den(x, t)
+    with pytest.raises(RuntimeError, match="consumed inside the fused kernels"):
+        _ = den.conv2[2].v
+    functional.reset_net(den)
+    assert torch.equal(den(x, t), a)
+    functional.reset_net(den)
+
+
+def test_forward_with_loss_returns_the_3_tuple_in_both_modes():
+    m, _ = make_vqvae(4, 128, seed=1)
+    vq = m.vq_layer
+    g = torch.Generator().manual_seed(0)
+    x = (torch.rand((4, 3, 16, 7, 7), generator=g) < 0.2).float().cuda()
+    q, loss, idx = vq.forward_with_loss(x)
+    functional.reset_net(m)
+    assert q.shape == x.shape and idx.shape == (3 * 49,) and idx.dtype == torch.int64 and loss.dim() == 0
+    vq.train()
+    xg = x.clone().requires_grad_(True)
+    q2, loss2, idx2 = vq.forward_with_loss(xg)
+    functional.reset_net(m)
+    assert q2.shape == x.shape and idx2.shape == (3 * 49,) and idx2.dtype == torch.int64
+    assert torch.equal(idx2, idx)                                        # same feature, same codebook
+    loss2.backward()
+    assert vq.embeddings.weight.grad is not None and float(vq.embeddings.weight.grad.abs().sum()) > 0
+    vq.eval()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_model_on_a_non_current_device_runs_there():
+    """a model moved with .to('cuda:1') while cuda:0 is current must launch on cuda:1's stream."""
+    assert torch.cuda.current_device() == 0
+    den, _ = make_denoiser(4, 128, seed=0, device="cuda:1")
+    den0, _ = make_denoiser(4, 128, seed=0, device="cuda:0")
+    x = torch.full((2, 1, 7, 7), 128.0)
+    t = torch.full((2,), 7, dtype=torch.long)
+    a = den(x.to("cuda:1"), t.to("cuda:1"))
+    b = den0(x.cuda(), t.cuda())
+    assert a.device.index == 1 and torch.equal(a.cpu(), b.cpu())
+    functional.reset_net(den); functional.reset_net(den0)

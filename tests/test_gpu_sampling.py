@@ -111,19 +111,15 @@ def test_sample_loop_vs_oracle_and_sharding():
     x = ab.sample(temp=0.9, sample_steps=49, seed=5)
     assert x.shape == (b, 1, 7, 7) and x.dtype == torch.int64
     assert int(x.max()) < K and int(x.min()) >= 0                    # no mask token left (t=1 unmasks everything)
-    # oracle driven by the same Philox stream
+    # oracle driven by the same Philox stream: every image identical step by step, or its first divergence attributed
+    # to a near-threshold neuron / near-tie draw (tests/_sample_parity.py; the benchmark-scale cases are in
+    # tests/test_gpu_sample_parity.py)
+    from _sample_parity import run_case
+    rep = run_case("small_T2", den, sd, ab, T=T, K=K, hw=7, n_global=b, shard_base=0, check=list(range(b)), temp=0.9,
+                   seed=5)
+    assert rep["identical"] + len(rep["diverged"]) == b and rep["identical"] >= b - 1, rep
     plan = ab.plan(b)
     step_inc = plan.inc_u + plan.inc_e
-    uni = lambda step, n: torch.from_numpy(philox.uniform(5, step * step_inc, n, sms, thr))
-    expo = lambda step, rows, k: torch.from_numpy(
-        philox.exponential(5, step * step_inc + plan.inc_u, rows * k, sms, thr)).reshape(rows, k)
-    rec = []
-    x_ref = O.sample(sd, T, b, (7, 7), K, K, 0.9, 49, uni, expo, record=rec)
-    agree = float((x.cpu() == x_ref).float().mean())
-    # identical stream and margin-exact spikes: trajectories coincide unless a near-tie flips a draw, after which
-    # that image's later draws may differ; require that at least 3 of the 4 images are identical end to end
-    same_imgs = int((x.cpu() == x_ref).reshape(b, -1).all(dim=1).sum())
-    assert same_imgs >= b - 1, (agree, same_imgs)
     # reproducible, and consumes torch's generator like the reference's two draws per step
     torch.manual_seed(5)
     gen = torch.cuda.default_generators[torch.cuda.current_device()]

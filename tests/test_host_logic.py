@@ -221,3 +221,68 @@ def test_lazy_memory_states_follow_the_memory_protocol():
     assert torch.equal(c.v, torch.arange(6.0).reshape(2, 3))
     n.v = base.LazyState(build)
     assert [tuple(v.shape) for v in n.memories()] == [(2, 3)]
+
+
+# ---- round-2 host-side checks ---------------------------------------------------------------------------
+def test_memout_coefficients_bound_to_another_T_raise_on_the_fused_path():
+    """engine._coef_array is what the fused plans use for the memout coefficients: a buffer bound to another T must
+    raise the reference's broadcasting RuntimeError (SURVEY.md finding 1), never truncate or zero-pad."""
+    from spiking_diffusion_b200 import engine
+    from spiking_diffusion_b200.snn_model.snn_layers import MembraneOutputLayer
+    coef16 = MembraneOutputLayer(16).coef
+    arr = engine._coef_array(coef16, 16)
+    assert len(arr) == 16 and abs(arr[15] - 1.0) < 1e-7 and abs(arr[14] - 0.8) < 1e-7
+    for T in (4, 8, 32):
+        with pytest.raises(RuntimeError, match=r"size of tensor a \(%d\) must match the size of tensor b \(16\)" % T):
+            engine._coef_array(coef16, T)
+
+
+def test_plan_caches_stay_out_of_deepcopy_and_pickle_and_key_covers_hyperparameters():
+    import copy
+    import pickle
+    from spiking_diffusion_b200 import engine
+    from spiking_diffusion_b200.snn_model import SNN_VQVAE, DummyModel, AbsorbingDiffusion
+    den = DummyModel(1, 128, T=4)
+    den._plans = {"key": 1, "plan": (lambda: 0)}            # a stand-in for ctypes pointers / CUDA graphs: not picklable
+    ab = AbsorbingDiffusion(den, mask_id=128)
+    ab._plans = {"key": 2, "plan": (lambda: 0)}
+    vae = SNN_VQVAE(1, 16, 128, torch.tensor(1.0), T=4)
+    vae._plans = {"key": 3, "plan": (lambda: 0)}
+    for m in (den, ab, vae):
+        c = copy.deepcopy(m)
+        assert c._plans == {} and m._plans != {}
+        assert pickle.loads(pickle.dumps(m))._plans == {}
+        m.invalidate_plans()
+        assert m._plans == {}
+    k0 = engine.module_cache_key(den)
+    den.conv3[2].tau = 4.0                                    # a LIF hyper-parameter baked into the plan
+    k1 = engine.module_cache_key(den)
+    den.conv2[1].eps = 1e-3                                   # BN eps is folded into scale/shift
+    k2 = engine.module_cache_key(den)
+    assert k0 != k1 and k1 != k2
+    with torch.no_grad():
+        den.conv2[0].weight.mul_(2.0)                         # in-place tensor op bumps _version
+    assert engine.module_cache_key(den) != k2
+
+
+def test_consumed_state_blocks_reads_until_reset():
+    from spiking_diffusion_b200.activation_based import base, functional, neuron
+    n = neuron.LIFNode()
+    assert n.memory_is_reset("v")
+    n.v = base.ConsumedState("test.node")
+    assert not n.memory_is_reset("v")
+    with pytest.raises(RuntimeError, match="consumed inside the fused kernels"):
+        _ = n.v
+    functional.reset_net(n)
+    assert n.memory_is_reset("v") and n.v == 0.0
+
+
+def test_device_helpers_without_gpu():
+    from spiking_diffusion_b200 import _lib
+    assert _lib.first_cuda_device(torch.zeros(2), [torch.zeros(1)], torch.nn.Linear(2, 2)) is None
+    assert _lib.ptr(None) is None
+
+    @_lib.on_device_of
+    def f(x, k=1):
+        return x + k
+    assert float(f(torch.zeros(1), k=2)) == 2.0

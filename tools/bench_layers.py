@@ -9,7 +9,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
-from spiking_diffusion_b200 import engine  # noqa: E402
+from spiking_diffusion_b200 import _lib, engine  # noqa: E402
 
 CONFIGS = [
     {},
@@ -30,6 +30,7 @@ def main():
             if k.startswith("SD_TC_"):
                 del os.environ[k]
         os.environ.update(cfg)
+        _lib.check(_lib.lib().sd_debug_tc_reload_knobs())   # the library reads the SD_TC_* knobs once per process
         try:
             dp = engine.DenoiserPlan(den, T, b, hw, hw, nsplit=2)
         except Exception as e:  # noqa: BLE001

@@ -8,8 +8,14 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from spiking_diffusion_b200 import _lib  # noqa: E402
+# the cycle stamps exist only in the -DSD_TRACE build of the library (build/libsd_b200_trace.so); build it here (on the
+# CPU box, before gpurun) or on the GPU box, and make the package load it instead of the shipped library
+if not os.path.exists(_lib.TRACE_LIB_PATH) or os.environ.get("SD_TRACE_REBUILD"):
+    _lib.build(trace=True)
+os.environ["SD_B200_LIB"] = _lib.TRACE_LIB_PATH
 import bench  # noqa: E402
-from spiking_diffusion_b200 import _lib, engine  # noqa: E402
+from spiking_diffusion_b200 import engine  # noqa: E402
 
 
 def main():
