@@ -180,7 +180,7 @@ def test_get_data_for_diff_reproduces_the_no_reset_state_leak():
         s, v = O.lif_multi_step(cur, state.get(name))
         state[name] = v
         return s
-    ref = []
+    ref, margins = [], []
     for img, _ in batches:
         x = (img - 0.5).unsqueeze(0).repeat(T, 1, 1, 1, 1)
         q = "encoder.snn_convs."
@@ -189,8 +189,10 @@ def test_get_data_for_diff_reproduces_the_no_reset_state_leak():
         x = lif("e3", O.conv_bn(x, sd, q + "6", q + "7"))
         feat = O.vq_feature(x, sd["vq_layer.alpha"])
         ref.append(O.vq_code_indices(feat.reshape(-1, 16), sd["vq_layer.embeddings.weight"]).reshape(B, 7, 7))
-    assert float((got[0] != ref[0]).float().mean()) <= 5e-3
-    assert float((got[1] != ref[1]).float().mean()) <= 5e-3
+        margins.append(O.vq_margin(feat.reshape(-1, 16), sd["vq_layer.embeddings.weight"]).reshape(B, 7, 7))
+    # the contract's index rule: bit-exact wherever the oracle's top-2 distance gap exceeds 1e-4 (north_star)
+    for g_, r_, m_ in zip(got, ref, margins):
+        assert int(((g_ != r_) & (m_ > SPIKE_MARGIN)).sum()) == 0, int((g_ != r_).sum())
     # the leak is real: encoding batch 2 from a reset model gives different indices for some tokens
     fresh = get_data_for_diff(batches[1:], m)[0]
     functional.reset_net(m)
@@ -238,7 +240,9 @@ def test_fused_eval_forward_keeps_the_lif_state_protocol():
     for n, vr in zip(nodes[4:], v_ref[4:]):
         assert n.v.shape == vr.shape
     e2, rec2, idx2 = m(xs, img)              # not reset: continues from the (materialised) states, module by module
-    assert float((idx2 != idx_ref2).float().mean()) <= 0.02
+    # both passes are ours (fused chain + lazily converted states vs module by module): same kernels' arithmetic except
+    # the tensor-core route of the stride-2 layers, so at most a near-threshold token may move
+    assert int((idx2 != idx_ref2).sum()) <= 1, int((idx2 != idx_ref2).sum())
     functional.reset_net(m)
     assert m._all_lif_reset()
 
