@@ -275,10 +275,11 @@ int sd_sample_step(const float* logits, int64_t* x_t, uint8_t* unmasked, int64_t
                    int64_t n_tokens, int K, int t, float temp, uint64_t seed, uint64_t offset_uniform,
                    uint64_t offset_exponential, int64_t token_base, int64_t n_tokens_global, void* stream);
 
-/* Same step with (seed, base generator offset) read from DEVICE memory (rng_dev[0] = seed, rng_dev[1] = offset, a
- * multiple of 4) and the two per-step offsets given relative to that base: the launch parameters are then
- * independent of the RNG state, so a CUDA graph of the whole sampling loop can be replayed with a new stream by
- * rewriting 16 bytes of device memory. */
+/* Same step with (seed, base generator offset, extra token base) read from DEVICE memory (rng_dev[0] = seed,
+ * rng_dev[1] = offset, a multiple of 4, rng_dev[2] = number of tokens added to token_base) and the two per-step
+ * offsets given relative to that base: the launch parameters are then independent of the RNG state and of the
+ * position of the batch in the global stream, so ONE CUDA graph of the whole sampling loop can be replayed with a new
+ * stream, or for the next chunk of a large batch, by rewriting 24 bytes of device memory. */
 int sd_sample_step_dev(const float* logits, int64_t* x_t, uint8_t* unmasked, int64_t* x0_hat_or_null,
                        int64_t n_tokens, int K, int t, float temp, const uint64_t* rng_dev,
                        uint64_t rel_offset_uniform, uint64_t rel_offset_exponential, int64_t token_base,

@@ -206,27 +206,29 @@ _tls = threading.local()
 def ptr(t) -> Optional[int]:
     if t is None:
         return None
-    if t.is_cuda:
+    d = t.get_device()          # -1 for a CPU tensor (host-side coefficient arrays never come through here)
+    if d >= 0:
         seen = getattr(_tls, "devices", None)
         if seen is None:
             seen = _tls.devices = set()
-        seen.add(t.device.index)
+        seen.add(d)
     return t.data_ptr()
 
 
 def stream_ptr() -> int:
     import torch
     seen = getattr(_tls, "devices", None)
-    cur = torch.cuda.current_device()
+    cur = torch._C._cuda_getDevice()
     if seen:
-        devs = sorted(seen)
-        seen.clear()
-        if len(devs) > 1:
-            raise ValueError(f"all tensors of one libsd_b200 call must live on one CUDA device, got cuda:{devs}")
-        if devs[0] != cur:
+        if len(seen) > 1 or cur not in seen:
+            devs = sorted(seen)
+            seen.clear()
+            if len(devs) > 1:
+                raise ValueError(f"all tensors of one libsd_b200 call must live on one CUDA device, got cuda:{devs}")
             raise RuntimeError(f"tensors live on cuda:{devs[0]} but the current CUDA device is cuda:{cur}; "
                                "run the call under torch.cuda.device(tensor.device) (the public entry points do)")
-    return torch.cuda.current_stream(cur).cuda_stream
+        seen.clear()
+    return torch._C._cuda_getCurrentRawStream(cur)
 
 
 def first_cuda_device(*objs):

@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(256) sample_step_kernel(const float* __restric
     cu.seed = ce.seed = seed;
     cu.offset4 += base4;
     ce.offset4 += base4;
+    token_base += (int64_t)rng_dev[2];   // where this call's tokens start in the global stream (chunked large batches)
   }
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;

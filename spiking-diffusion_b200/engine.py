@@ -199,6 +199,22 @@ class FusedLayer:
             mac = d.C_in * d.C_out * d.kh * d.kw * d.H_out * d.W_out
         return 2 * mac * d.B * d.T
 
+    def executed_tensor_ops(self) -> int:
+        """Tensor-pipe operations the layer really issues (2 x MAC of the problem as run x weight terms): the upsampled /
+        stride-1 restatements run 4x the algorithm's MACs, the T-summed read-out 1/T of them, exact weights 2 fp16
+        terms (or 3 int8 digits) per algorithmic MAC.  0 for the CUDA-core kernels."""
+        if self.impl != "tc":
+            return 0
+        d = self.desc
+        mac = d.C_in * d.C_out * d.kh * d.kw * d.H_out * d.W_out * d.B * (d.in_T if d.in_kind == _lib.IN_STF else d.T)
+        return 2 * mac * d.nsplit
+
+    def mma_kind(self) -> str:
+        if self.impl != "tc":
+            return "cuda cores (fp32)"
+        return {1: "tcgen05 kind::f16, 1 fp16 weight term", 2: "tcgen05 kind::f16, 2 exact fp16 weight terms (2 passes)",
+                3: "tcgen05 kind::i8, 3 int8 weight digits at twice the rate (1.5 pass equivalents), exact int32 accumulation"}[self.desc.nsplit]
+
     def alloc_out(self) -> torch.Tensor:
         d = self.desc
         if d.out_kind == _lib.OUT_LIF:
@@ -428,9 +444,13 @@ class SamplerPlan:
 
     def sample(self, temp: float, sample_steps: int, seed: int, offset0: int = 0,
                x_init: Optional[torch.Tensor] = None, unmasked_init: Optional[torch.Tensor] = None,
-               use_graph: Optional[bool] = None, history: Optional[torch.Tensor] = None) -> torch.Tensor:
+               use_graph: Optional[bool] = None, history: Optional[torch.Tensor] = None,
+               extra_base: int = 0) -> torch.Tensor:
         """x_init / unmasked_init (host or device, [b,1,h,w] or flat): start from a partially unmasked grid
         instead of the all-mask grid of vq_diffusion.py:106-107; copied on the current stream (pinned host -> device).
+
+        extra_base: images added to the plan's shard_base for this call only (a large batch generated as consecutive
+        chunks by ONE plan and one captured graph; the value lives in device memory next to the RNG state).
 
         use_graph (default: env SD_SAMPLER_GRAPH, on): the loop (h*w steps x 8 kernels x sub-batches) is captured once
         per (temp, steps) into a CUDA graph and replayed; the Philox (seed, offset) pair lives in device memory
@@ -447,13 +467,21 @@ class SamplerPlan:
             if history.shape != (sample_steps, self.n_tokens) or history.dtype != torch.int64 or not history.is_cuda:
                 raise ValueError(f"history must be a CUDA int64 tensor of shape ({sample_steps}, {self.n_tokens})")
             use_graph = False
+        extra_tokens = int(extra_base) * self.h * self.w
+        if self.token_base + extra_tokens + self.n_tokens > self.n_tokens_global:
+            raise ValueError("extra_base moves the shard past the end of the global batch")
         if not use_graph:
-            self._enqueue(temp, sample_steps, seed, offset0, x_init is None, unmasked_init is None, history=history)
+            saved = self.token_base
+            self.token_base += extra_tokens
+            try:
+                self._enqueue(temp, sample_steps, seed, offset0, x_init is None, unmasked_init is None, history=history)
+            finally:
+                self.token_base = saved
             return self.x_t.view(self.b, 1, self.h, self.w)
         if not hasattr(self, "rng_dev"):
-            self.rng_dev = torch.zeros(2, dtype=torch.int64, device=self.x_t.device)
+            self.rng_dev = torch.zeros(3, dtype=torch.int64, device=self.x_t.device)
             self._graphs = {}
-        state = np.array([int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset0)], dtype=np.uint64).view(np.int64)
+        state = np.array([int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset0), extra_tokens], dtype=np.uint64).view(np.int64)
         self.rng_dev.copy_(torch.from_numpy(state))
         key = (float(temp), int(sample_steps), x_init is None, unmasked_init is None)
         g = self._graphs.get(key)

@@ -129,6 +129,10 @@ class AbsorbingDiffusion(engine.PlanCacheMixin, Sampler):
         self.mask_schedule = "random"
         self.loss_type = "reweighted_elbo"
         self._plans = {}
+        # larger n_samples are generated as consecutive chunks of this many images by one plan (activations of a chunk
+        # stay close to the L2 size; the chunks are slices of ONE global Philox stream, so the result does not depend
+        # on the chunk size)
+        self.max_plan_batch = 4096
 
     def sample_time(self, b, device):
         t = torch.randint(1, self.num_timesteps + 1, (b,), device=device).long()
@@ -180,6 +184,16 @@ class AbsorbingDiffusion(engine.PlanCacheMixin, Sampler):
                                                                   shard_base, nsplit=m.nsplit)}
         return self._plans["plan"]
 
+    def _tail_plan(self, n, n_global, shard_base):
+        """Plan for the ragged last chunk of a chunked batch (kept beside the main plan, same invalidation key)."""
+        key = ("tail", n, n_global, shard_base, self._plans.get("key"))
+        if self._plans.get("tail_key") != key:
+            m, (h, w) = self._denoise_fn, self.shape
+            self._plans["tail_key"] = key
+            self._plans["tail"] = engine.SamplerPlan(m, m.T, n, h, w, int(self.mask_id), n_global, shard_base,
+                                                     nsplit=m.nsplit)
+        return self._plans["tail"]
+
     @on_device_of
     @torch.no_grad()
     def sample(self, temp=1.0, sample_steps=None, seed=None, offset=0, n_global=None, shard_base: int = 0,
@@ -196,12 +210,26 @@ class AbsorbingDiffusion(engine.PlanCacheMixin, Sampler):
         b = int(self.n_samples)
         if sample_steps is None:
             raise TypeError("unsupported operand type(s) for +: 'NoneType' and 'int'")  # the reference's failure mode
-        plan = self.plan(b, n_global, shard_base)
+        n_global = b if n_global is None else int(n_global)
+        chunk = int(self.max_plan_batch)
+        if b > chunk and (x_init is not None or unmasked_init is not None or history is not None):
+            raise ValueError(f"x_init / unmasked_init / history are per-plan buffers: use n_samples <= {chunk}")
+        plan = self.plan(min(b, chunk), n_global, shard_base)
         if seed is None:
             gen = torch.cuda.default_generators[torch.cuda.current_device()]
             seed, offset = gen.initial_seed(), gen.get_offset()
             gen.set_offset(offset + plan.offset_advance(sample_steps))
-        x_t = plan.sample(float(temp), int(sample_steps), int(seed), int(offset), x_init, unmasked_init,
-                          history=history)
+        if b <= chunk:
+            x_t = plan.sample(float(temp), int(sample_steps), int(seed), int(offset), x_init, unmasked_init,
+                              history=history).clone()
+        else:
+            parts, lo = [], 0
+            while lo < b:
+                n = min(chunk, b - lo)
+                p = plan if n == chunk else self._tail_plan(n, n_global, shard_base + lo)
+                parts.append(p.sample(float(temp), int(sample_steps), int(seed), int(offset),
+                                      extra_base=lo if n == chunk else 0).clone())
+                lo += n
+            x_t = torch.cat(parts)
         functional.reset_net(self._denoise_fn)
-        return x_t.clone()
+        return x_t

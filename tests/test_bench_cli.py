@@ -9,6 +9,7 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 
 
 def run(*args, timeout=600):
@@ -17,7 +18,7 @@ def run(*args, timeout=600):
 
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
-    r = run("--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-batch", "2")
+    r = run("--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-batch", "2", "--quick")
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -27,12 +28,17 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "cfg2" in d["config"]["workload"] and d["vs_baseline"] is None
+    # the reference arm describes the SAME workload as our arm (the driver compares the config objects)
+    import argparse
+    import bench
+    a = argparse.Namespace(workload="cfg2", temp=1.0)
+    assert d["config"] == bench.base_config(a, bench.WORKLOADS["cfg2"], 1)
 
 
 def test_reference_arm_runs_on_rank_zero_only():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
-                        "--warmup", "1", "--cpu-batch", "2"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+                        "--warmup", "1", "--cpu-batch", "2", "--quick"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 

@@ -144,3 +144,20 @@ def test_sample_then_decode_end_to_end():
     img = engine.to_uint8(pred)
     assert img.shape == (b, 1, 28, 28) and img.dtype == torch.uint8
     assert 0 < float(pred.abs().max()) <= 1.0 and float(pred.std()) > 0.01
+
+
+def test_chunked_large_batch_equals_one_plan():
+    """n_samples above AbsorbingDiffusion.max_plan_batch is generated as consecutive chunks by one plan (one captured
+    graph; the chunk's position in the global stream lives in device memory): the result must not depend on it."""
+    T, K, b = 2, 128, 8
+    den, _ = make_denoiser(T, K, seed=2)
+    ab = AbsorbingDiffusion(den, mask_id=K, shape=(7, 7), n_samples=b)
+    whole = ab.sample(temp=1.0, sample_steps=49, seed=21)
+    ab.max_plan_batch = 3                        # chunks of 3, 3 and a ragged 2
+    ab.invalidate_plans()
+    parts = ab.sample(temp=1.0, sample_steps=49, seed=21)
+    assert parts.shape == whole.shape and torch.equal(parts, whole)
+    # also as a shard of a larger global batch
+    ab.n_samples = 6
+    lo = ab.sample(temp=1.0, sample_steps=49, seed=21, n_global=b, shard_base=0)
+    assert torch.equal(lo, whole[:6])
