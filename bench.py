@@ -604,7 +604,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--temp", type=float, default=1.0)
-    ap.add_argument("--nsplit", type=int, default=2, choices=[1, 2, 3])
+    ap.add_argument("--nsplit", type=int, default=3, choices=[1, 2, 3],
+                    help="weight representation of the tcgen05 layers: 3 int8 digits (default), 2 fp16 terms, 1 fp16 term")
     ap.add_argument("--cpu-batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="headline only (quick experiments)")

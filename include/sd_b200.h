@@ -62,6 +62,13 @@ int64_t sd_stf_bytes(int T, int B, int C, int H, int W); /* bytes of one STF ten
 /* fp32 [T,B,C,H,W] (reference layout, SJ/activation_based/layer.py:164-173) <-> STF */
 int sd_stf_from_nchw(const float* x, void* stf, int T, int B, int C, int H, int W, void* stream);
 int sd_stf_to_nchw(const void* stf, float* x, int T, int B, int C, int H, int W, void* stream);
+/* STF8: the u8 spike format of the kind::i8 layers, [T][2][C/16][R_alloc][16] (rows as in STF; per timestep the planes
+ * of s in {0,1} and of 128*s in {0,128}; same byte count as STF, sd_stf_bytes).  Conversions from / to the reference's
+ * fp32 [T, B, C, H, W] spike tensors, for API boundaries and tests (precedent for packed spikes:
+ * SJ/activation_based/tensor_cache.py:13-90).  C must be a multiple of 16. */
+int sd_stf8_from_nchw(const float* x, void* stf8, int T, int B, int C, int H, int W, void* stream);
+int sd_stf8_to_nchw(const void* stf8, float* x, int T, int B, int C, int H, int W, void* stream);
+
 /* Zero-insertion 2x upsampling of an STF tensor: out (T, B, C, 2H, 2W) with out[.., 2y, 2x] = in[.., y, x] and zeros
  * elsewhere.  ConvTranspose2d(k=3, s=2, p=1, output_padding=1) (R/snn_model/vae_model.py:139-146) equals a stride-1
  * 3x3 convolution with flipped taps of this tensor, which is how the decoder runs on sd_conv_lif_tc. */
@@ -140,15 +147,18 @@ int sd_vq_gather(const int64_t* idx, const float* codebook, float* out_nchw, int
 enum {
   SD_IN_REAL_CONST = 0, /* fp32 [B, C_in, H_in, W_in], identical at every timestep (R/main.py:133 repeat) */
   SD_IN_REAL_SEQ = 1,   /* fp32 [T, B, C_in, H_in, W_in] */
-  SD_IN_STF = 2         /* fp16 STF spikes (or T-summed spike counts when in_T == 1) */
+  SD_IN_STF = 2,        /* fp16 STF spikes (or T-summed spike counts when in_T == 1) */
+  SD_IN_STF8 = 3        /* u8 STF8 spikes: [T][2][C/16][R_alloc][16], per timestep the planes of s in {0,1} and of
+                           128*s in {0,128}; operand of the kind::i8 layers (sd_conv_lif_tc with nsplit = 3) */
 };
 enum {
   SD_OUT_LIF = 0,       /* BN affine -> LIF over T -> spikes (STF) [+ optional T-sum STF] */
   SD_OUT_REAL_SEQ = 1,  /* affine only -> fp32 [T, B, C_out, H_out, W_out] (un-fused layer.Conv2d) */
   SD_OUT_MEMOUT_TANH = 2, /* affine -> sum_t 0.8^(T-1-t) y_t -> tanh -> fp32 [B, C_out, H_out, W_out]
                              (decoder tail, R/snn_model/vae_model.py:152-153,186) */
-  SD_OUT_MEAN_T = 3     /* affine -> sum_t y_t / T -> fp32 [B, H_out, W_out, C_out] (channels last)
+  SD_OUT_MEAN_T = 3,    /* affine -> sum_t y_t / T -> fp32 [B, H_out, W_out, C_out] (channels last)
                              (denoiser read-out, R/snn_model/vq_diffusion.py:205-206) */
+  SD_OUT_LIF8 = 4       /* like SD_OUT_LIF with the spikes written as STF8 (u8); the optional T-sum stays fp16 STF */
 };
 
 typedef struct sd_conv_desc {
@@ -165,7 +175,8 @@ typedef struct sd_conv_desc {
                             torch.cat((x5, x1), dim=2), R/snn_model/vq_diffusion.py:205) */
   float tau, v_threshold, v_reset;
   int hard_reset;        /* LIFNode(v_reset=None) <=> 0 */
-  int nsplit;            /* tc only: fp16 terms per fp32 weight (1 or 2), see sd_conv_pack_weights_tc */
+  int nsplit;            /* tc only: 1 or 2 = fp16 terms per fp32 weight (kind::f16); 3 = three int8 digits of a 22-bit
+                            fixed-point weight (kind::i8, exact int32 accumulation), see sd_conv_pack_weights_tc */
   int concurrent;        /* tc only, tuning hint: how many launches of this size the caller keeps in flight on
                             different streams (0 or 1 = this launch has the GPU to itself).  A lone small batch is
                             cut into narrower N tiles to occupy more SMs; concurrent sub-batches are not. */

@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 # Exported symbols of include/sd_b200.h (tests check that the library exports exactly these).
 SYMBOLS = [
     "sd_last_error", "sd_version", "sd_device_info", "sd_stf_guard", "sd_stf_rows", "sd_stf_bytes",
-    "sd_stf_from_nchw", "sd_stf_to_nchw", "sd_stf_upsample2x", "sd_stf_subsample2x", "sd_channel_affine", "sd_state_convert", "sd_lif_forward", "sd_lif_backward", "sd_memout", "sd_vq_feature", "sd_vq_lookup",
+    "sd_stf_from_nchw", "sd_stf_to_nchw", "sd_stf8_from_nchw", "sd_stf8_to_nchw", "sd_stf_upsample2x", "sd_stf_subsample2x", "sd_channel_affine", "sd_state_convert", "sd_lif_forward", "sd_lif_backward", "sd_memout", "sd_vq_feature", "sd_vq_lookup",
     "sd_vq_gather", "sd_conv_weight_bytes_simt", "sd_conv_weight_bytes_tc", "sd_conv_workspace_bytes", "sd_conv_weight_layout_tc", "sd_conv_pack_weights_simt",
     "sd_conv_pack_weights_tc", "sd_conv_lif_simt", "sd_conv_lif_tc", "sd_conv_tc_supported", "sd_debug_tc_trace", "sd_debug_tc_reload_knobs", "sd_conv_wgrad_workspace_bytes", "sd_conv_wgrad",
     "sd_bn_train_forward", "sd_bn_backward", "sd_bn_local_stats", "sd_bn_backward_reduce", "sd_bn_backward_apply", "sd_philox_uniform",
@@ -106,8 +106,8 @@ class ConvArgs(ctypes.Structure):
                 ("workspace", ctypes.c_void_p)]
 
 
-IN_REAL_CONST, IN_REAL_SEQ, IN_STF = 0, 1, 2
-OUT_LIF, OUT_REAL_SEQ, OUT_MEMOUT_TANH, OUT_MEAN_T = 0, 1, 2, 3
+IN_REAL_CONST, IN_REAL_SEQ, IN_STF, IN_STF8 = 0, 1, 2, 3
+OUT_LIF, OUT_REAL_SEQ, OUT_MEMOUT_TANH, OUT_MEAN_T, OUT_LIF8 = 0, 1, 2, 3, 4
 SD_ERR_INVALID, SD_ERR_CUDA, SD_ERR_NO_DEVICE, SD_ERR_UNSUPPORTED = 1, 2, 3, 4
 
 _lib: Optional[ctypes.CDLL] = None
@@ -125,6 +125,8 @@ def _declare(lib: ctypes.CDLL) -> None:
         "sd_stf_bytes": (i64, [i, i, i, i, i]),
         "sd_stf_from_nchw": (i, [vp, vp, i, i, i, i, i, vp]),
         "sd_stf_to_nchw": (i, [vp, vp, i, i, i, i, i, vp]),
+        "sd_stf8_from_nchw": (i, [vp, vp, i, i, i, i, i, vp]),
+        "sd_stf8_to_nchw": (i, [vp, vp, i, i, i, i, i, vp]),
         "sd_stf_upsample2x": (i, [vp, vp, i, i, i, i, i, vp]),
         "sd_stf_subsample2x": (i, [vp, vp, i, i, i, i, i, vp]),
         "sd_channel_affine": (i, [vp, vp, vp, vp, i64, i, i64, vp]),

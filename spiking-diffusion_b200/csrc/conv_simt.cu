@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(256) conv_real_const_lif_kernel(const SimtPara
       cnt[j] = 0.f;
     }
     __half* outp = (__half*)p.out;
+    const bool out8 = d.out_kind == SD_OUT_LIF8;
 #pragma unroll
     for (int t = 0; t < TMAX; ++t) {
       if (t < T) {
@@ -360,10 +361,23 @@ __global__ void __launch_bounds__(256) conv_real_const_lif_kernel(const SimtPara
             v[j] = d.hard_reset ? (s ? d.v_reset : h) : (s ? __fsub_rn(h, d.v_threshold) : h);
           }
           cnt[j] += s ? 1.f : 0.f;
-          const uint32_t bits = s ? 0x3C00u : 0u;
-          if (j & 1) pk[j >> 1] |= bits << 16; else pk[j >> 1] = bits;
+          if (out8) {       // STF8: one byte per spike, 8 channels = half of a 16-byte row
+            const uint32_t bit = (s ? 1u : 0u) << (8 * (j & 3));
+            if (j & 3) pk[j >> 2] |= bit; else pk[j >> 2] = bit;
+          } else {
+            const uint32_t bits = s ? 0x3C00u : 0u;
+            if (j & 1) pk[j >> 1] |= bits << 16; else pk[j >> 1] = bits;
+          }
         }
-        *reinterpret_cast<uint4*>(outp + gout.at(t, Cout8, co, orow)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (out8) {
+          const int64_t plane = (int64_t)(Cout8 >> 1) * gout.R_alloc * 16;
+          uint8_t* o = (uint8_t*)p.out + (int64_t)(t * 2) * plane + ((int64_t)(chunk >> 1) * gout.R_alloc + orow) * 16 +
+                       (chunk & 1) * 8;
+          *reinterpret_cast<uint2*>(o) = make_uint2(pk[0], pk[1]);
+          *reinterpret_cast<uint2*>(o + plane) = make_uint2(pk[0] << 7, pk[1] << 7);      // the 128*s plane
+        } else {
+          *reinterpret_cast<uint4*>(outp + gout.at(t, Cout8, co, orow)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
       }
     }
     if (p.v) {
@@ -680,14 +694,18 @@ int validate_conv_desc(const sd_conv_desc* d) {
   SD_REQUIRE(d->B >= 1 && d->C_in >= 1 && d->C_out >= 1 && d->H_in >= 1 && d->W_in >= 1 && d->H_out >= 1 &&
                  d->W_out >= 1, "conv: non-positive dimension");
   SD_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->stride >= 1 && d->pad >= 0, "conv: bad kernel/stride/padding");
-  SD_REQUIRE(d->in_kind >= SD_IN_REAL_CONST && d->in_kind <= SD_IN_STF, "conv: bad in_kind %d", d->in_kind);
-  SD_REQUIRE(d->out_kind >= SD_OUT_LIF && d->out_kind <= SD_OUT_MEAN_T, "conv: bad out_kind %d", d->out_kind);
+  SD_REQUIRE(d->in_kind >= SD_IN_REAL_CONST && d->in_kind <= SD_IN_STF8, "conv: bad in_kind %d", d->in_kind);
+  SD_REQUIRE(d->out_kind >= SD_OUT_LIF && d->out_kind <= SD_OUT_LIF8, "conv: bad out_kind %d", d->out_kind);
+  if (d->in_kind == SD_IN_STF8) SD_REQUIRE(d->in_T == d->T && d->C_in0 == d->C_in && d->C_in % 16 == 0,
+                                           "conv: STF8 input needs in_T == T, one segment, C_in %% 16 == 0");
+  if (d->out_kind == SD_OUT_LIF8) SD_REQUIRE(d->C_out % 16 == 0, "conv: STF8 output needs C_out %% 16 == 0");
   if (d->in_kind == SD_IN_STF) {
     SD_REQUIRE(d->in_T == d->T || d->in_T == 1, "conv: in_T must be T or 1");
     SD_REQUIRE(d->C_in0 >= 1 && d->C_in0 <= d->C_in, "conv: C_in0 out of range");
     SD_REQUIRE(d->C_in0 == d->C_in || d->C_in0 % 8 == 0, "conv: concat boundary must be a multiple of 8");
   }
-  if (d->out_kind == SD_OUT_LIF) SD_REQUIRE(d->tau > 1.0f, "LIFNode requires tau > 1, got %f", (double)d->tau);
+  if (d->out_kind == SD_OUT_LIF || d->out_kind == SD_OUT_LIF8)
+    SD_REQUIRE(d->tau > 1.0f, "LIFNode requires tau > 1, got %f", (double)d->tau);
   // output size consistent with torch's formulas (nn.Conv2d / nn.ConvTranspose2d docs)
   if (!d->transposed) {
     SD_REQUIRE(d->H_out == (d->H_in + 2 * d->pad - d->kh) / d->stride + 1 &&
@@ -743,7 +761,13 @@ int sd_conv_lif_simt(const sd_conv_desc* d, const sd_conv_args* a, void* stream)
   int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   cudaStream_t st = as_stream(stream);
-  if (d->in_kind == SD_IN_REAL_CONST && d->out_kind == SD_OUT_LIF && !d->transposed && d->C_out % 8 == 0) {
+  if (d->in_kind == SD_IN_STF8 || (d->out_kind == SD_OUT_LIF8 && !(d->in_kind == SD_IN_REAL_CONST && !d->transposed))) {
+    set_error("conv_simt: the u8 spike format (STF8) is produced by the constant-input layer and consumed by "
+              "sd_conv_lif_tc (nsplit = 3) only");
+    return SD_ERR_UNSUPPORTED;
+  }
+  if (d->in_kind == SD_IN_REAL_CONST && (d->out_kind == SD_OUT_LIF || d->out_kind == SD_OUT_LIF8) && !d->transposed &&
+      d->C_out % 8 == 0) {
     int64_t n8 = (int64_t)d->B * d->H_out * d->W_out * (d->C_out / 8);
     int64_t bl = (n8 + 255) / 256;
     if (bl > cap) bl = cap;

@@ -55,7 +55,11 @@ constexpr int kMaxBStages = 8;
 constexpr uint32_t kSmemBudget = 220 * 1024;
 
 struct TcConfig {
-  int T_acc;       // accumulators per pass (min(T, 4) timesteps for LIF, 1 for the T-summed linear read-out)
+  int i8;          // 1: kind::i8 path (nsplit == 3): u8 spikes x three s8 weight digits, two int32 accumulators
+                   // (hi = 128*d0 + d1, lo = d2) per timestep, exact integer accumulation
+  int accs;        // TMEM accumulators per timestep (1, or 2 for i8)
+  int rowch;       // channels per 16-byte operand row: 8 (fp16) or 16 (u8 / s8)
+  int T_acc;       // timesteps per pass (min(T, 4) for fp16 LIF, 2 for i8, 1 for the T-summed linear read-out)
   int pair;        // 1: 2-CTA clusters, tcgen05.mma.cta_group::2 (M = 256 per pair), half of every B block per CTA
   int n_tchunks;   // passes per tile: T / T_acc.  T = 8 / 16 run as 2 / 4 passes of 4 timesteps at N = 128 with the
                    // membrane potential carried between passes in an L2-resident fp32 plane, instead of one pass at
@@ -82,6 +86,7 @@ struct TcParams {
   const float* scale;
   const float* shift;
   __half* out_spk;
+  uint8_t* out_spk8;        // i8 path: spikes as STF8 ([T][2][C/16][R_alloc][16] u8: planes of s and of 128*s)
   __half* out_sum;
   float* out_real;
   float* cur;               // tpar mode: currents [T][C_out/8][R_alloc][8] fp32 (workspace)
@@ -161,6 +166,18 @@ __device__ __forceinline__ void tc_mma_f16_masked(uint32_t d_tmem, uint64_t ades
       "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
       : "memory");
 }
+// kind::i8: u8 / s8 operands (K = 32 per instruction), int32 accumulators
+__device__ __forceinline__ void tc_mma_i8_masked(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate, uint32_t m0, uint32_t m1, uint32_t m2,
+                                                 uint32_t m3) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+      : "memory");
+}
 // ---- cta_group::2 (two SMs of a cluster pair share one M = 256 MMA) ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -193,6 +210,17 @@ __device__ __forceinline__ void tc_mma_f16_masked_pair(uint32_t d_tmem, uint64_t
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8, %9, %10, %11, %12}, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]),
+      "r"(m[4]), "r"(m[5]), "r"(m[6]), "r"(m[7])
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8_masked_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                      uint32_t accumulate, const uint32_t (&m)[8]) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8, %9, %10, %11, %12}, p;\n\t"
       "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]),
       "r"(m[4]), "r"(m[5]), "r"(m[6]), "r"(m[7])
       : "memory");
@@ -255,10 +283,16 @@ struct PipeState {
 // PAIR: the CTA is one half of a 2-CTA cluster; the pair computes an M = 256 tile with tcgen05.mma.cta_group::2 issued by
 // the leader (rank 0).  Each SM stages its own 128 A rows and HALF of the B tile (N/2 rows), which cuts the
 // shared-memory operand fetch per MMA from A 4 KB + B 4 KB to A 4 KB + B 2 KB per SM.
+// NSPLIT == 3 selects the kind::i8 path: operands are bytes (16 channels per 16-byte row, K = 32 per MMA, KSTEPS =
+// KBLK / 32); per timestep the A stage holds the planes of s and of 128*s, the B stage three digit blocks
+// [d0 | d1 | d2] with w_fix = 256 * (128 * d0 + d1) + d2, and TMEM two int32 accumulators: hi += A128 x d0 + A1 x d1,
+// lo += A1 x d2.  Three K = 32 MMAs cover 32 input channels where the fp16 path needs four K = 16 MMAs.
 template <int NSPLIT, int KSTEPS, bool PAIR>
 __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcConfig& c = p.c;
+  constexpr bool I8 = NSPLIT == 3;
+  constexpr int ACCS = I8 ? 2 : 1;            // TMEM accumulators per timestep
   // barrier block (first 256 B), then A stages, then B stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t bar_base = smem_u32(bars);
@@ -324,13 +358,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     const int tl = tile_of(unit);
     return PAIR ? 2 * (tl / c.n_tiles) + (int)cta_rank : tl / c.n_tiles;
   };
-  const int chunks = c.KBLK >> 3;            // 8-channel chunks per K block
+  const int chunks = I8 ? c.KBLK >> 4 : c.KBLK >> 3;   // 16-byte-row chunks (8 fp16 / 16 u8 channels) per K block
+  const int planes_t = I8 ? 2 * chunks : chunks * c.ndx;   // planes per timestep in an A stage
   const uint32_t plane_bytes = (uint32_t)c.rows_ld * 16u;
 
   if (warp == 8) {
     // ===== A producer =====
     PipeState st;
-    const int ncopy = c.T_acc * chunks * c.ndx;
+    const int ncopy = c.T_acc * planes_t;
     for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
       // an odd number of M tiles leaves the last pair with a phantom second tile: it re-reads the last real tile (its
       // epilogue writes nothing because its rows are >= R_valid)
@@ -347,12 +382,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
         const int C8 = seg1 ? p.C8_1 : p.C8_0;
         const int chunk0 = (seg1 ? kb - c.c0_blocks : kb) * chunks;
         for (int i = lane; i < ncopy; i += 32) {
-          const int pl = i / c.ndx, dxi = i - pl * c.ndx;          // plane (t, chunk) and its dx copy
-          const int tl = pl / chunks, ch = pl - tl * chunks;
-          const int t = tch * c.T_acc + tl;
-          const int dx = c.ndx == 3 ? dxi - 1 : 0;
-          const __half* g = src + ((((int64_t)t * C8 + chunk0 + ch) * p.R_alloc) + p.G + row0 - c.halo + dx) * 8;
-          bulk_g2s(a_base + st.stage * c.a_stage_bytes + (uint32_t)i * plane_bytes, g, plane_bytes, a_full(st.stage));
+          if constexpr (I8) {
+            // stage order [t][scale: s, 128*s][chunk]; global STF8 order [t][scale][C/16][row][16]
+            const int tl = i / planes_t, rem = i - tl * planes_t;
+            const int sc = rem / chunks, ch = rem - sc * chunks;
+            const int t = tch * c.T_acc + tl;
+            const uint8_t* g = reinterpret_cast<const uint8_t*>(src) +
+                               ((((int64_t)(t * 2 + sc) * C8 + chunk0 + ch) * p.R_alloc) + p.G + row0 - c.halo) * 16;
+            bulk_g2s(a_base + st.stage * c.a_stage_bytes + (uint32_t)i * plane_bytes, g, plane_bytes, a_full(st.stage));
+          } else {
+            const int pl = i / c.ndx, dxi = i - pl * c.ndx;          // plane (t, chunk) and its dx copy
+            const int tl = pl / chunks, ch = pl - tl * chunks;
+            const int t = tch * c.T_acc + tl;
+            const int dx = c.ndx == 3 ? dxi - 1 : 0;
+            const __half* g = src + ((((int64_t)t * C8 + chunk0 + ch) * p.R_alloc) + p.G + row0 - c.halo + dx) * 8;
+            bulk_g2s(a_base + st.stage * c.a_stage_bytes + (uint32_t)i * plane_bytes, g, plane_bytes, a_full(st.stage));
+          }
         }
         st.advance(c.a_stages);
       }
@@ -403,7 +448,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     const uint32_t a_lo_const = (((uint32_t)c.ndx * plane_bytes) >> 4) << 16;   // LBO: next 8-channel chunk
     const uint32_t b_lbo = (uint32_t)(PAIR ? c.N_TILE / 2 : c.N_TILE) * 16u;   // rows of B staged in THIS CTA
     const uint32_t b_lo_const = (b_lbo >> 4) << 16;
-    const uint32_t a_step_t = ((uint32_t)(chunks * c.ndx) * plane_bytes) >> 4;
+    const uint32_t a_step_t = ((uint32_t)planes_t * plane_bytes) >> 4;
+    const uint32_t a_off_128 = ((uint32_t)chunks * plane_bytes) >> 4;          // i8: from the s planes to the 128*s planes
     const uint32_t a_step_k = ((uint32_t)(2 * c.ndx) * plane_bytes) >> 4;
     const uint32_t b_step_sp = ((uint32_t)chunks * b_lbo) >> 4;
     const uint32_t b_step_k = (2u * b_lbo) >> 4;
@@ -433,7 +479,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
       mbar_wait(acc_empty(sc.stage), sc.phase ^ 1);
       tc_fence_after();
       if (trace && lane == 0 && trace_it < 7) trace[3 + trace_it * 8 + 0] = clock64();
-      const uint32_t d_base = tmem_base + (uint32_t)(sc.stage * c.T_acc * c.N_TILE);
+      const uint32_t d_base = tmem_base + (uint32_t)(sc.stage * c.T_acc * ACCS * c.N_TILE);
       for (int kb = 0; kb < c.num_kblocks; ++kb) {
         const long long w0 = trace ? clock64() : 0;
         mbar_wait(a_full(sa.stage), sa.phase);
@@ -463,19 +509,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
             for (int w = 0; w < MW; ++w)
               km[w] = (dy < 0 ? m_up[w] : (dy > 0 ? m_dn[w] : 0u)) | (kx == 0 ? m_lf[w] : (kx == 2 ? m_rt[w] : 0u));
             for (int t = 0; t < c.T_acc; ++t) {
-#pragma unroll
-              for (int sp = 0; sp < NSPLIT; ++sp) {
+              if constexpr (I8) {
+                const uint32_t d_lo = d + (uint32_t)c.N_TILE;
 #pragma unroll
                 for (int ks = 0; ks < KSTEPS; ++ks) {
-                  const uint64_t adesc = ((uint64_t)desc_hi << 32) | (a_lo + ks * a_step_k);
-                  const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (b_lo0 + sp * b_step_sp + ks * b_step_k);
-                  if (PAIR) tc_mma_f16_masked_pair(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first, km);
-                  else if (dbg & 4) tc_mma_f16(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first);   // timing experiment
-                  else tc_mma_f16_masked(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first, km[0], km[1], km[2], km[3]);
+                  const uint64_t a1 = ((uint64_t)desc_hi << 32) | (a_lo + ks * a_step_k);
+                  const uint64_t a128 = ((uint64_t)desc_hi << 32) | (a_lo + a_off_128 + ks * a_step_k);
+                  const uint64_t bd0 = ((uint64_t)desc_hi << 32) | (b_lo0 + ks * b_step_k);
+                  const uint64_t bd1 = ((uint64_t)desc_hi << 32) | (b_lo0 + b_step_sp + ks * b_step_k);
+                  const uint64_t bd2 = ((uint64_t)desc_hi << 32) | (b_lo0 + 2 * b_step_sp + ks * b_step_k);
+                  const uint32_t acc0 = ks != 0 ? 1u : first;
+                  if (PAIR) {
+                    tc_mma_i8_masked_pair(d, a128, bd0, p.idesc, acc0, km);        // hi += (128 s) x d0
+                    tc_mma_i8_masked_pair(d, a1, bd1, p.idesc, 1u, km);            // hi += s x d1
+                    tc_mma_i8_masked_pair(d_lo, a1, bd2, p.idesc, acc0, km);       // lo += s x d2
+                  } else {
+                    tc_mma_i8_masked(d, a128, bd0, p.idesc, acc0, km[0], km[1], km[2], km[3]);
+                    tc_mma_i8_masked(d, a1, bd1, p.idesc, 1u, km[0], km[1], km[2], km[3]);
+                    tc_mma_i8_masked(d_lo, a1, bd2, p.idesc, acc0, km[0], km[1], km[2], km[3]);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int sp = 0; sp < NSPLIT; ++sp) {
+#pragma unroll
+                  for (int ks = 0; ks < KSTEPS; ++ks) {
+                    const uint64_t adesc = ((uint64_t)desc_hi << 32) | (a_lo + ks * a_step_k);
+                    const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (b_lo0 + sp * b_step_sp + ks * b_step_k);
+                    if (PAIR) tc_mma_f16_masked_pair(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first, km);
+                    else if (dbg & 4) tc_mma_f16(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first);   // timing experiment
+                    else tc_mma_f16_masked(d, adesc, bdesc, p.idesc, (sp | ks) != 0 ? 1u : first, km[0], km[1], km[2], km[3]);
+                  }
                 }
               }
               a_lo += a_step_t;
-              d += (uint32_t)c.N_TILE;
+              d += (uint32_t)(ACCS * c.N_TILE);
             }
             if (PAIR) { tc_commit_pair(b_empty(sb.stage)); if (ti == 8) tc_commit_pair(a_empty(sa.stage)); }
             else { tc_commit(b_empty(sb.stage)); if (ti == 8) tc_commit(a_empty(sa.stage)); }
@@ -519,7 +587,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
       mbar_wait(acc_full(sc.stage), sc.phase);
       tc_fence_after();
       if (trace && threadIdx.x == 0 && trace_it < 7) trace[3 + trace_it * 8 + 4] = clock64();
-      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc.stage * c.T_acc * c.N_TILE);
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc.stage * c.T_acc * ACCS * c.N_TILE);
+      // accumulator of local timestep tl, 16 columns from cc: one TMEM load (fp32), or for i8 two (int32 hi and lo)
+      // that conv_value() merges into the fp32 convolution value in place: (float)(256 * hi + lo), a single rounding of
+      // the exact integer sum (the per-channel scaling guarantees that 256 * hi + lo fits an int32)
+      auto ld_acc = [&](int tl, int cc, uint32_t (&a)[16], uint32_t (&lo)[16]) {
+        tc_ld16(t_base + (uint32_t)(tl * ACCS * c.N_TILE + cc), a);
+        if constexpr (I8) tc_ld16(t_base + (uint32_t)((tl * ACCS + 1) * c.N_TILE + cc), lo);
+      };
+      auto conv_value = [&](uint32_t (&a)[16], uint32_t (&lo)[16]) {
+        tc_ld_wait_on(a);
+        if constexpr (I8) {
+          tc_ld_wait_on(lo);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) a[j] = __float_as_uint(__int2float_rn((int)a[j] * 256 + (int)lo[j]));
+        }
+      };
       for (int cc = col_lo; cc < col_hi; cc += 16) {
         const int n = n0 + cc;  // first output channel of this 16-column group (warp-uniform)
         if (n >= p.Cout) continue;  // zero-padded tail of the last N tile
@@ -534,9 +617,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
         if (c.tpar) {
           // T-parallel mode: this pass only delivers the input currents x[t] = conv * scale + shift of its timesteps
           for (int tl = 0; tl < c.T_acc; ++tl) {
-            uint32_t acc[16];
-            tc_ld16(t_base + (uint32_t)(tl * c.N_TILE + cc), acc);
-            tc_ld_wait_on(acc);
+            uint32_t acc[16], acc_lo[16];
+            ld_acc(tl, cc, acc, acc_lo);
+            conv_value(acc, acc_lo);
             if (valid) {
               const int t = tch * c.T_acc + tl;
               float* o = p.cur + (((int64_t)t * p.Cout8 + (n >> 3)) * p.R_alloc + p.G + r) * 8;
@@ -613,7 +696,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
               packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&s2);
               if (want_sum) cnt2[j >> 1] = __hadd2(cnt2[j >> 1], s2);
             }
-            if (valid && n < p.Cout && p.out_spk != nullptr && !(dbg & 1)) {
+            if constexpr (I8) {
+              if (valid && n < p.Cout && p.out_spk8 != nullptr) {
+                // fp16 {0, 1.0} pairs -> bytes {0, 1}: bit 10 of each half is the spike; one 16-byte row = 16 channels.
+                // The 128*s plane of the same timestep lies Cout/16 planes further.
+                uint32_t w8[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  w8[k] = __byte_perm((packed[2 * k] >> 10) & 0x00010001u, (packed[2 * k + 1] >> 10) & 0x00010001u, 0x6420);
+                const int t = tch * c.T_acc + tl;
+                const int64_t plane = (int64_t)(p.Cout8 >> 1) * p.R_alloc * 16;
+                uint8_t* o = p.out_spk8 + (int64_t)(t * 2) * plane + (((int64_t)(n >> 4)) * p.R_alloc + p.G + r) * 16;
+                *reinterpret_cast<uint4*>(o) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+                *reinterpret_cast<uint4*>(o + plane) = make_uint4(w8[0] << 7, w8[1] << 7, w8[2] << 7, w8[3] << 7);
+              }
+            } else if (valid && n < p.Cout && p.out_spk != nullptr && !(dbg & 1)) {
               const int t = tch * c.T_acc + tl;
               __half* o = p.out_spk + (((int64_t)t * p.Cout8 + (n >> 3)) * p.R_alloc + p.G + r) * 8;
               *reinterpret_cast<uint4*>(o) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -622,18 +719,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
           };
           // two register sets: the TMEM load of timestep t + 1 is in flight while timestep t is computed
           auto lif_all = [&](auto fast_tag) {
-            uint32_t accA[16], accB[16];
+            uint32_t accA[16], accB[16], loA[16], loB[16];
             const bool ld = !(dbg & 2);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) accA[j] = accB[j] = 0u;
-            if (ld) tc_ld16(t_base + (uint32_t)cc, accA);
+            for (int j = 0; j < 16; ++j) accA[j] = accB[j] = loA[j] = loB[j] = 0u;
+            if (ld) ld_acc(0, cc, accA, loA);
             for (int tl = 0; tl < c.T_acc; tl += 2) {
-              tc_ld_wait_on(accA);
-              if (tl + 1 < c.T_acc && ld) tc_ld16(t_base + (uint32_t)((tl + 1) * c.N_TILE + cc), accB);
+              conv_value(accA, loA);
+              if (tl + 1 < c.T_acc && ld) ld_acc(tl + 1, cc, accB, loB);
               lif_step(fast_tag, accA, tl);
               if (tl + 1 < c.T_acc) {
-                tc_ld_wait_on(accB);
-                if (tl + 2 < c.T_acc && ld) tc_ld16(t_base + (uint32_t)((tl + 2) * c.N_TILE + cc), accA);
+                conv_value(accB, loB);
+                if (tl + 2 < c.T_acc && ld) ld_acc(tl + 2, cc, accA, loA);
                 lif_step(fast_tag, accB, tl + 1);
               }
             }
@@ -747,6 +844,15 @@ __global__ void __launch_bounds__(256) lif_from_currents_kernel(const TcParams p
       if (p.out_spk != nullptr)
         *reinterpret_cast<uint4*>(p.out_spk + (int64_t)t * p.Cout8 * p.R_alloc * 8 + off) =
             make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      if (p.out_spk8 != nullptr) {
+        // STF8: this thread's 8 channels are one half of a 16-byte row of the s plane and of the 128*s plane
+        const uint32_t w0 = __byte_perm((packed[0] >> 10) & 0x00010001u, (packed[1] >> 10) & 0x00010001u, 0x6420);
+        const uint32_t w1 = __byte_perm((packed[2] >> 10) & 0x00010001u, (packed[3] >> 10) & 0x00010001u, 0x6420);
+        const int64_t plane = (int64_t)(p.Cout8 >> 1) * p.R_alloc * 16;
+        uint8_t* o = p.out_spk8 + (int64_t)(t * 2) * plane + ((ch >> 1) * p.R_alloc + p.G + r) * 16 + (ch & 1) * 8;
+        *reinterpret_cast<uint2*>(o) = make_uint2(w0, w1);
+        *reinterpret_cast<uint2*>(o + plane) = make_uint2(w0 << 7, w1 << 7);
+      }
     }
     if (p.out_sum != nullptr) {
       const uint32_t* pk = reinterpret_cast<const uint32_t*>(cnt2);
@@ -808,6 +914,16 @@ static const TcKnobs& knobs() {
 static int tc_supported(const sd_conv_desc* d, const char** why) {
   *why = "";
   if (d->transposed || d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != 1) { *why = "only 3x3 stride 1 pad 1"; return 0; }
+  const bool i8 = d->nsplit == 3;
+  if (i8) {
+    if (d->in_kind != SD_IN_STF8) { *why = "nsplit = 3 (int8 digits) takes STF8 (u8) spikes"; return 0; }
+    if (d->out_kind != SD_OUT_LIF8) { *why = "nsplit = 3 (int8 digits) writes STF8 spikes (out_kind LIF8)"; return 0; }
+    if (d->T % 2 || d->in_T != d->T || d->T > 16) { *why = "int8 path needs an even T <= 16 and in_T == T"; return 0; }
+    if (d->C_in0 != d->C_in || d->C_in % 32 || d->C_out % 16) { *why = "int8 path needs C_in % 32 == 0, C_out % 16 == 0, one input segment"; return 0; }
+    if (d->H_in != d->H_out || d->W_in != d->W_out) { *why = "output grid must equal input grid"; return 0; }
+    if (d->W_in + 2 > 64) { *why = "grid too wide for the row-shift window"; return 0; }
+    return 1;
+  }
   if (d->in_kind != SD_IN_STF) { *why = "input must be STF spikes"; return 0; }
   if (d->H_in != d->H_out || d->W_in != d->W_out) { *why = "output grid must equal input grid"; return 0; }
   if (d->out_kind != SD_OUT_LIF && d->out_kind != SD_OUT_MEAN_T) { *why = "out_kind must be LIF or MEAN_T"; return 0; }
@@ -816,14 +932,77 @@ static int tc_supported(const sd_conv_desc* d, const char** why) {
   const int c0 = d->C_in0, c1 = d->C_in - d->C_in0;
   if (c0 % 16 || c1 % 16) { *why = "channel segments must be multiples of 16"; return 0; }
   if (d->C_out % 16) { *why = "C_out must be a multiple of 16"; return 0; }
-  if (d->nsplit < 1 || d->nsplit > 2) { *why = "nsplit must be 1 or 2"; return 0; }
+  if (d->nsplit < 1 || d->nsplit > 2) { *why = "nsplit must be 1 or 2 (fp16 terms) or 3 (int8 digits)"; return 0; }
   if (d->W_in + 2 > 64) { *why = "grid too wide for the row-shift window"; return 0; }
   return 1;
+}
+
+// kind::i8 configuration: 2 timesteps per pass (hi + lo accumulators of 2 timesteps fill the 512 TMEM columns at
+// N = 128), T / 2 passes with the membrane potential carried through the state plane, K block 64 (or 32) channels.
+static int tc_config_i8(const sd_conv_desc* d, TcConfig* c) {
+  check_device();
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  c->T_acc = 2;
+  c->n_tchunks = d->T / 2;
+  c->ndx = 1;
+  const int64_t rows = (int64_t)d->B * d->H_in * d->W_in;
+  const int m_tiles = (int)((rows + kTileRows - 1) / kTileRows);
+  int n_tile = 128;
+  const int conc = d->concurrent > 1 ? d->concurrent : 1;
+  const bool can_pair = knobs().pair && m_tiles >= 2;
+  // a single M tile cannot be paired: narrower N tiles spread it over more SMs (same rule as the fp16 path)
+  while (n_tile > 32 && knobs().small_batch_split && !can_pair &&
+         (int64_t)m_tiles * ((d->C_out + n_tile - 1) / n_tile) * 2 * conc <= sms && d->C_out > n_tile / 2)
+    n_tile /= 2;
+  c->tpar = 0;
+  if (c->n_tchunks > 1 && d->concurrent <= 1 && knobs().tpar) {
+    const int64_t pair_units = (((int64_t)m_tiles + 1) / 2) * ((d->C_out + 127) / 128);
+    if (pair_units * 4 <= sms) { c->tpar = 1; n_tile = 128; }
+  }
+  if (knobs().ntile > 0) n_tile = knobs().ntile;
+  while (n_tile > 32 && n_tile / 2 >= d->C_out) n_tile /= 2;
+  if (!(n_tile == 32 || n_tile == 64 || n_tile == 128)) { set_error("conv_tc(i8): bad N tile %d", n_tile); return SD_ERR_UNSUPPORTED; }
+  c->N_TILE = n_tile;
+  c->pair = (knobs().pair && n_tile == 128 && m_tiles >= 2) ? 1 : 0;
+  c->acc_stages = 512 / (c->T_acc * 2 * n_tile) >= 2 ? 2 : 1;
+  c->halo = d->W_in + 1;
+  c->rows_ld = kTileRows + 2 * c->halo;
+  bool found = false;
+  static const int kblks[2] = {64, 32};
+  for (int i = 0; i < 2 && !found; ++i) {
+    const int kblk = kblks[i];
+    if (knobs().kblk && kblk != knobs().kblk) continue;
+    if (d->C_in % kblk) continue;
+    c->a_stage_bytes = (uint32_t)c->T_acc * 2 * (kblk / 16) * c->rows_ld * 16;
+    c->b_stage_bytes = 3u * (kblk / 16) * (c->pair ? n_tile / 2 : n_tile) * 16;   // per CTA
+    const uint32_t b_ref = 3u * (kblk / 16) * 128 * 16;      // batch-independent fit test (see the fp16 path)
+    if (2 * c->a_stage_bytes + 4 * b_ref + 1024 > kSmemBudget) continue;
+    c->KBLK = kblk;
+    found = true;
+  }
+  if (!found) { set_error("conv_tc(i8): no K block fits shared memory"); return SD_ERR_UNSUPPORTED; }
+  c->a_stages = (int)((kSmemBudget - 1024 - 4 * c->b_stage_bytes) / c->a_stage_bytes);
+  if (c->a_stages > 3) c->a_stages = 3;
+  const uint32_t left = kSmemBudget - 1024 - c->a_stages * c->a_stage_bytes;
+  c->b_stages = (int)(left / c->b_stage_bytes);
+  if (c->b_stages > kMaxBStages) c->b_stages = kMaxBStages;
+  c->smem_bytes = 1024 + c->a_stages * c->a_stage_bytes + c->b_stages * c->b_stage_bytes;
+  if (c->smem_bytes < 117u * 1024u) c->smem_bytes = 117u * 1024u;
+  c->n_tiles = (d->C_out + n_tile - 1) / n_tile;
+  c->m_tiles = m_tiles;
+  c->c0_blocks = d->C_in / c->KBLK;
+  c->num_kblocks = d->C_in / c->KBLK;
+  return SD_OK;
 }
 
 static int tc_config(const sd_conv_desc* d, TcConfig* c) {
   const char* why;
   if (!tc_supported(d, &why)) { set_error("conv_tc: unsupported descriptor: %s", why); return SD_ERR_UNSUPPORTED; }
+  const bool i8 = d->nsplit == 3;
+  c->i8 = i8 ? 1 : 0;
+  c->accs = i8 ? 2 : 1;
+  c->rowch = i8 ? 16 : 8;
+  if (i8) return tc_config_i8(d, c);
   c->T_acc = d->out_kind == SD_OUT_LIF ? d->T : 1;
   if (d->out_kind == SD_OUT_LIF && d->T > 4 && d->T % 4 == 0 && knobs().tchunk) c->T_acc = 4;
   if (d->out_kind == SD_OUT_LIF) {
@@ -993,6 +1172,78 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, const int* __restric
   }
 }
 
+// ---- int8 digits -----------------------------------------------------------------------------------------------
+// Per output channel the weights become 22-bit fixed point: w_fix = rint(w * 2^e) with e the largest exponent such that
+// max|w_fix| < 2^21 and sum_k |w_fix_k| < 2^31 (then 256 * hi + lo = sum of the active w_fix can never overflow an
+// int32, whatever fires).  w_fix = 256 * (128 * d0 + d1) + d2 with d0, d2 in [-128, 127], d1 in [-64, 63].
+// chan_scale = 2^-e is folded into the BN scale by the caller (exact).
+__global__ void tc_chan_exp_i8_kernel(const float* __restrict__ w, int Cin, float* __restrict__ chan_scale, int* __restrict__ e_out) {
+  const int co = blockIdx.x;
+  float m = 0.f;
+  double l1 = 0.0;
+  for (int i = threadIdx.x; i < Cin * 9; i += blockDim.x) {
+    const float a = fabsf(w[(int64_t)co * Cin * 9 + i]);
+    m = fmaxf(m, a);
+    l1 += (double)a;
+  }
+  __shared__ float red[256];
+  __shared__ double red1[256];
+  red[threadIdx.x] = m;
+  red1[threadIdx.x] = l1;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s]);
+      red1[threadIdx.x] += red1[threadIdx.x + s];      // fixed tree order: deterministic
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int e = 0;
+    if (red[0] > 0.f && isfinite(red[0])) {
+      int ex;
+      frexpf(red[0], &ex);              // max = f * 2^ex, f in [0.5, 1)  ->  max * 2^(21 - ex) in [2^20, 2^21)
+      e = 21 - ex;
+      // L1 bound with the rounding slack of every term: sum|w| * 2^e + 0.5 * K < 2^31
+      const double room = 2147483647.0 - 0.5 * (double)Cin * 9.0 - 1.0;
+      while (ldexp(red1[0], e) >= room) --e;
+    }
+    e_out[co] = e;
+    chan_scale[co] = ldexpf(1.0f, -e);
+  }
+}
+
+// layout [n_tile][k_block][tap][half][digit 3][chunk (16 channels)][n (N_TILE / halves)][16 bytes]
+__global__ void tc_pack_i8_kernel(const float* __restrict__ w, const int* __restrict__ e_in, int8_t* __restrict__ out,
+                                  int Cout, int Cin, int N_TILE, int KBLK, int n_tiles, int num_kblocks, int halves) {
+  const int chunks = KBLK / 16;
+  const int NH = N_TILE / halves;
+  const int64_t total = (int64_t)n_tiles * num_kblocks * 9 * 3 * chunks * N_TILE * 16;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int j = (int)(i % 16);
+    int64_t r = i / 16;
+    int n = (int)(r % NH); r /= NH;
+    int ch = (int)(r % chunks); r /= chunks;
+    int dg = (int)(r % 3); r /= 3;
+    int hf = (int)(r % halves); r /= halves;
+    int tap = (int)(r % 9); r /= 9;
+    int kb = (int)(r % num_kblocks);
+    int nt = (int)(r / num_kblocks);
+    const int co = nt * N_TILE + hf * NH + n;
+    const int ci = kb * KBLK + ch * 16 + j;
+    int val = 0;
+    if (co < Cout) {
+      const int wf = (int)rintf(ldexpf(w[((int64_t)co * Cin + ci) * 9 + tap], e_in[co]));   // exact scaling, one rounding
+      const int d2 = ((wf + 128) & 255) - 128;                 // balanced low digit in [-128, 127]
+      const int hi = (wf - d2) / 256;                          // exact
+      const int d1 = ((hi + 64) & 127) - 64;                   // [-64, 63]
+      const int d0 = (hi - d1) / 128;                          // [-128, 127] because |wf| < 2^21
+      val = dg == 0 ? d0 : (dg == 1 ? d1 : d2);
+    }
+    out[i] = (int8_t)val;
+  }
+}
+
 }  // namespace sd
 
 using namespace sd;
@@ -1046,7 +1297,7 @@ int64_t sd_conv_workspace_bytes(const sd_conv_desc* d) {
 int64_t sd_conv_weight_layout_tc(const sd_conv_desc* d) {
   TcConfig c;
   if (!d || validate_conv_desc(d) != SD_OK || tc_config(d, &c) != SD_OK) return -1;
-  return ((int64_t)c.N_TILE << 16) | ((int64_t)c.KBLK << 4) | (int64_t)c.pair;
+  return ((int64_t)c.N_TILE << 16) | ((int64_t)c.KBLK << 4) | ((int64_t)c.i8 << 1) | (int64_t)c.pair;
 }
 
 int64_t sd_conv_weight_bytes_tc(const sd_conv_desc* d) {
@@ -1067,6 +1318,16 @@ int sd_conv_pack_weights_tc(const sd_conv_desc* d, const float* w, void* packed,
   cudaStream_t st = as_stream(stream);
   const int64_t main_bytes = (int64_t)c.n_tiles * c.num_kblocks * 9 * c.b_stage_bytes * (c.pair ? 2 : 1);
   int* e_buf = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(packed) + main_bytes);
+  if (c.i8) {
+    tc_chan_exp_i8_kernel<<<d->C_out, 256, 0, st>>>(w, d->C_in, chan_scale_out, e_buf);
+    SD_LAUNCH_CHECK();
+    int64_t bl8 = (main_bytes + 255) / 256;
+    if (bl8 > (int64_t)sm_count() * 8) bl8 = (int64_t)sm_count() * 8;
+    tc_pack_i8_kernel<<<(unsigned)bl8, 256, 0, st>>>(w, e_buf, (int8_t*)packed, d->C_out, d->C_in, c.N_TILE, c.KBLK,
+                                                     c.n_tiles, c.num_kblocks, c.pair ? 2 : 1);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+  }
   tc_chan_exp_kernel<<<d->C_out, 256, 0, st>>>(w, d->C_in, chan_scale_out, e_buf);
   SD_LAUNCH_CHECK();
   const int64_t total = main_bytes / 2;
@@ -1111,16 +1372,19 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
     return SD_ERR_INVALID;
   }
   if (d->out_kind == SD_OUT_LIF) { p.out_spk = (__half*)a->out; p.out_sum = (__half*)a->out_sum; }
+  else if (d->out_kind == SD_OUT_LIF8) { p.out_spk8 = (uint8_t*)a->out; p.out_sum = (__half*)a->out_sum; }
   else p.out_real = (float*)a->out;
   StfGeom g(d->B, d->H_in, d->W_in);
   p.R_alloc = g.R_alloc; p.G = g.G; p.R_valid = (int64_t)d->B * g.P;
-  p.C8_0 = d->C_in0 / 8; p.C8_1 = (d->C_in - d->C_in0) / 8;
+  p.C8_0 = d->C_in0 / c.rowch; p.C8_1 = (d->C_in - d->C_in0) / c.rowch;   // 16-byte-row chunks per input segment
   p.Cout = d->C_out; p.Cout8 = c8(d->C_out);
   p.T = d->T; p.H = d->H_in; p.W = d->W_in; p.Wp = g.Wp; p.P = g.P;
-  p.nsplit = d->nsplit; p.out_kind = d->out_kind; p.hard_reset = d->hard_reset;
+  p.nsplit = d->nsplit; p.out_kind = d->out_kind == SD_OUT_LIF8 ? SD_OUT_LIF : d->out_kind; p.hard_reset = d->hard_reset;
   p.tau = d->tau; p.v_th = d->v_threshold; p.v_reset = d->v_reset;
   // cute::UMMA::InstrDescriptor: c_format F32 (bit 4), a/b F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-  p.idesc = (1u << 4) | ((uint32_t)(c.N_TILE >> 3) << 17) | ((uint32_t)((c.pair ? 2 * kTileRows : kTileRows) >> 4) << 24);
+  // kind::i8: c_format S32 (2 at bit 4), a_format u8 (0 at bit 7), b_format s8 (1 at bit 10)
+  p.idesc = (c.i8 ? ((2u << 4) | (1u << 10)) : (1u << 4)) | ((uint32_t)(c.N_TILE >> 3) << 17) |
+            ((uint32_t)((c.pair ? 2 * kTileRows : kTileRows) >> 4) << 24);
   p.c = c;
 #ifdef SD_TRACE
   p.trace = g_tc_trace;
@@ -1167,8 +1431,10 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
     if (c.pair) SD_TC_LAUNCH_ONE(NS, KS, true);                 \
     else SD_TC_LAUNCH_ONE(NS, KS, false);                       \
   } while (0)
-  const int ks = c.KBLK / 16;
-  if (d->nsplit == 1) {
+  const int ks = c.i8 ? c.KBLK / 32 : c.KBLK / 16;
+  if (d->nsplit == 3) {
+    if (ks == 1) SD_TC_LAUNCH(3, 1); else SD_TC_LAUNCH(3, 2);
+  } else if (d->nsplit == 1) {
     if (ks == 1) SD_TC_LAUNCH(1, 1); else if (ks == 2) SD_TC_LAUNCH(1, 2); else SD_TC_LAUNCH(1, 4);
   } else {
     if (ks == 1) SD_TC_LAUNCH(2, 1); else if (ks == 2) SD_TC_LAUNCH(2, 2); else SD_TC_LAUNCH(2, 4);

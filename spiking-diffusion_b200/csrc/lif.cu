@@ -271,6 +271,46 @@ __global__ void stf_to_nchw_kernel(const __half* __restrict__ stf, float* __rest
   }
 }
 
+// STF8 (u8 spikes for the kind::i8 layers): [T][2][C/16][R_alloc][16]; plane 0 of a timestep holds s, plane 1 holds 128*s
+__global__ void stf8_from_nchw_kernel(const float* __restrict__ x, uint8_t* __restrict__ stf, int T, int B, int C, int H,
+                                      int W) {
+  StfGeom g(B, H, W);
+  const int C16 = C / 16;
+  const int64_t total = (int64_t)T * B * C * H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int xw = (int)(i % W);
+    int64_t r = i / W;
+    int y = (int)(r % H); r /= H;
+    int c = (int)(r % C); r /= C;
+    int b = (int)(r % B);
+    int t = (int)(r / B);
+    const uint8_t s = x[i] != 0.f ? 1 : 0;
+    const int64_t row = g.row(b, y, xw);
+    stf[(((int64_t)(t * 2) * C16 + (c >> 4)) * g.R_alloc + row) * 16 + (c & 15)] = s;
+    stf[(((int64_t)(t * 2 + 1) * C16 + (c >> 4)) * g.R_alloc + row) * 16 + (c & 15)] = (uint8_t)(s << 7);
+  }
+}
+
+// checks both planes: returns s from the s plane, and NaN where the 128*s plane disagrees (a format error shows up in tests)
+__global__ void stf8_to_nchw_kernel(const uint8_t* __restrict__ stf, float* __restrict__ x, int T, int B, int C, int H,
+                                    int W) {
+  StfGeom g(B, H, W);
+  const int C16 = C / 16;
+  const int64_t total = (int64_t)T * B * C * H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int xw = (int)(i % W);
+    int64_t r = i / W;
+    int y = (int)(r % H); r /= H;
+    int c = (int)(r % C); r /= C;
+    int b = (int)(r % B);
+    int t = (int)(r / B);
+    const int64_t row = g.row(b, y, xw);
+    const uint8_t s = stf[(((int64_t)(t * 2) * C16 + (c >> 4)) * g.R_alloc + row) * 16 + (c & 15)];
+    const uint8_t s128 = stf[(((int64_t)(t * 2 + 1) * C16 + (c >> 4)) * g.R_alloc + row) * 16 + (c & 15)];
+    x[i] = (s <= 1 && s128 == (uint8_t)(s << 7)) ? (float)s : __int_as_float(0x7fc00000);
+  }
+}
+
 // Zero-insertion 2x upsampling of a spike tensor: out[t, c, b, 2y, 2x] = in[t, c, b, y, x], every other pixel 0.
 // A stride-2 ConvTranspose2d(k=3, p=1, output_padding=1) is exactly a stride-1 3x3 convolution (pad 1, flipped taps)
 // of this tensor, which puts the decoder on the tcgen05 kernel.  One thread = one 16-byte (8-channel) element.
@@ -453,6 +493,28 @@ int sd_stf_from_nchw(const float* x, void* stf, int T, int B, int C, int H, int 
   SD_CUDA(cudaMemsetAsync(stf, 0, (size_t)sd_stf_bytes(T, B, C, H, W), st));
   int64_t n = (int64_t)T * B * C * H * W;
   stf_from_nchw_kernel<<<grid_for(n), 256, 0, st>>>(x, (__half*)stf, T, B, C, H, W);
+  SD_LAUNCH_CHECK();
+  return SD_OK;
+}
+
+int sd_stf8_from_nchw(const float* x, void* stf, int T, int B, int C, int H, int W, void* stream) {
+  SD_REQUIRE(T >= 1 && B >= 1 && C >= 16 && C % 16 == 0 && H >= 1 && W >= 1, "stf8_from_nchw: bad shape (C must be a multiple of 16)");
+  SD_REQUIRE(x && stf, "null pointer argument");
+  SD_DEVICE_OR_RETURN();
+  cudaStream_t st = as_stream(stream);
+  SD_CUDA(cudaMemsetAsync(stf, 0, (size_t)sd_stf_bytes(T, B, C, H, W), st));   // same byte count as the fp16 format
+  int64_t n = (int64_t)T * B * C * H * W;
+  stf8_from_nchw_kernel<<<grid_for(n), 256, 0, st>>>(x, (uint8_t*)stf, T, B, C, H, W);
+  SD_LAUNCH_CHECK();
+  return SD_OK;
+}
+
+int sd_stf8_to_nchw(const void* stf, float* x, int T, int B, int C, int H, int W, void* stream) {
+  SD_REQUIRE(T >= 1 && B >= 1 && C >= 16 && C % 16 == 0 && H >= 1 && W >= 1, "stf8_to_nchw: bad shape (C must be a multiple of 16)");
+  SD_REQUIRE(x && stf, "null pointer argument");
+  SD_DEVICE_OR_RETURN();
+  int64_t n = (int64_t)T * B * C * H * W;
+  stf8_to_nchw_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>((const uint8_t*)stf, x, T, B, C, H, W);
   SD_LAUNCH_CHECK();
   return SD_OK;
 }

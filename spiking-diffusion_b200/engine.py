@@ -83,6 +83,22 @@ def stf_from_nchw(x: torch.Tensor) -> torch.Tensor:
 
 
 @_lib.on_device_of
+def stf8_from_nchw(x: torch.Tensor) -> torch.Tensor:
+    """fp32 {0,1} spikes [T,B,C,H,W] -> STF8 (u8 planes of s and 128*s; the operand format of the kind::i8 layers)."""
+    T, B, C, H, W = x.shape
+    out = torch.empty(lib().sd_stf_bytes(T, B, C, H, W), dtype=torch.uint8, device=x.device)
+    check(lib().sd_stf8_from_nchw(ptr(x.contiguous().float()), ptr(out), T, B, C, H, W, stream_ptr()))
+    return out
+
+
+@_lib.on_device_of
+def stf8_to_nchw(stf8: torch.Tensor, T: int, B: int, C: int, H: int, W: int) -> torch.Tensor:
+    out = torch.empty((T, B, C, H, W), dtype=torch.float32, device=stf8.device)
+    check(lib().sd_stf8_to_nchw(ptr(stf8), ptr(out), T, B, C, H, W, stream_ptr()))
+    return out
+
+
+@_lib.on_device_of
 def stf_to_nchw(stf: torch.Tensor, T: int, B: int, C: int, H: int, W: int) -> torch.Tensor:
     out = torch.empty((T, B, C, H, W), dtype=torch.float32, device=stf.device)
     check(lib().sd_stf_to_nchw(ptr(stf), ptr(out), T, B, C, H, W, stream_ptr()))
@@ -150,6 +166,13 @@ class FusedLayer:
             d.tau, d.v_threshold, d.v_reset, d.hard_reset = 2.0, 1.0, 0.0, 1
         d.nsplit = nsplit
         d.concurrent = int(concurrent)
+        if nsplit == 3 and impl != "simt":
+            # kind::i8 layer: u8 spikes in and out (STF8)
+            if in_kind != _lib.IN_STF or out_kind != _lib.OUT_LIF:
+                raise ValueError("nsplit=3 (int8 weight digits) is a spike -> LIF layer")
+            d.in_kind, d.out_kind = _lib.IN_STF8, _lib.OUT_LIF8
+        if impl == "simt":
+            d.nsplit = 2                      # unused by the CUDA-core kernels
         self.desc = d
         self.algorithmic_flops = None   # set when the layer runs a mathematically equal but larger problem
         self.device = w.device
@@ -165,7 +188,7 @@ class FusedLayer:
         ws = L.sd_conv_workspace_bytes(ctypes.byref(d)) if impl == "tc" else 0
         self._ws = torch.empty(ws, dtype=torch.uint8, device=self.device) if ws else None
         self.layout = L.sd_conv_weight_layout_tc(ctypes.byref(d)) if impl == "tc" else 0
-        if (share is not None and share.impl == impl and share.desc.nsplit == nsplit and share.T == T
+        if (share is not None and share.impl == impl and share.desc.nsplit == d.nsplit and share.T == T
                 and share.layout == self.layout):
             # sub-batch plans reuse the packed weights when their tile configuration (the layout key) is the same
             self.wpack, self.scale, self.shift, self._coef = share.wpack, share.scale, share.shift, share._coef
@@ -217,6 +240,8 @@ class FusedLayer:
 
     def alloc_out(self) -> torch.Tensor:
         d = self.desc
+        if d.out_kind == _lib.OUT_LIF8:      # same byte count as the fp16 format; guard / pad rows must be zero
+            return torch.zeros(lib().sd_stf_bytes(d.T, d.B, d.C_out, d.H_out, d.W_out), dtype=torch.uint8, device=self.device)
         if d.out_kind == _lib.OUT_LIF:
             return stf_empty(d.T, d.B, d.C_out, d.H_out, d.W_out, self.device)
         if d.out_kind == _lib.OUT_REAL_SEQ:
@@ -262,13 +287,22 @@ class DenoiserPlan:
         mk = lambda seq, sh, **kw: FusedLayer(seq[0], seq[1] if len(seq) > 1 else None, seq[2] if len(seq) > 2 else None,
                                               T=T, B=b, H_in=h, W_in=w, nsplit=nsplit, share=sh,
                                               concurrent=concurrent, **kw)
-        self.l1 = mk(model.conv1, wf and wf.l1, in_kind=_lib.IN_REAL_CONST, out_kind=_lib.OUT_LIF, impl="simt")
-        self.l2 = mk(model.conv2, wf and wf.l2, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
-        self.l3 = mk(model.conv3, wf and wf.l3, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
-        self.l4 = mk(model.conv4, wf and wf.l4, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
-        self.l5 = mk(model.conv5, wf and wf.l5, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
-        self.l6 = mk(model.conv6, wf and wf.l6, in_kind=_lib.IN_STF, out_kind=_lib.OUT_MEAN_T, impl=impl, in_T=1,
-                     C_in0=256)
+        # nsplit = 3: conv2..conv5 on the kind::i8 tensor-core path (u8 spikes between the layers, three int8 weight
+        # digits, exact int32 accumulation: 3 MMAs per 32 input channels where two fp16 terms need 4).  It needs an even
+        # T; the read-out layer consumes T-summed counts (up to T per element) and stays on the fp16 path.
+        self.i8 = nsplit == 3 and T % 2 == 0 and impl != "simt"
+        ns = 3 if self.i8 else (2 if nsplit == 3 else nsplit)
+        self.l1 = mk(model.conv1, wf and wf.l1, in_kind=_lib.IN_REAL_CONST,
+                     out_kind=_lib.OUT_LIF8 if self.i8 else _lib.OUT_LIF, impl="simt")
+        mk_s = lambda seq, sh: FusedLayer(seq[0], seq[1], seq[2], T=T, B=b, H_in=h, W_in=w, nsplit=ns, share=sh,
+                                          concurrent=concurrent, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
+        self.l2 = mk_s(model.conv2, wf and wf.l2)
+        self.l3 = mk_s(model.conv3, wf and wf.l3)
+        self.l4 = mk_s(model.conv4, wf and wf.l4)
+        self.l5 = mk_s(model.conv5, wf and wf.l5)
+        self.l6 = FusedLayer(model.conv6[0], None, None, T=T, B=b, H_in=h, W_in=w, nsplit=2 if ns == 3 else ns,
+                             share=wf and wf.l6, concurrent=concurrent, in_kind=_lib.IN_STF, out_kind=_lib.OUT_MEAN_T,
+                             impl=impl, in_T=1, C_in0=256)
         self.layers = [self.l1, self.l2, self.l3, self.l4, self.l5, self.l6]
         self.xin = torch.empty((b, 2, h, w), dtype=torch.float32, device=dev)
         self.x1, self.x1s = self.l1.alloc_out(), self.l1.alloc_sum()
@@ -282,6 +316,8 @@ class DenoiserPlan:
     def spikes_nchw(self, buf: torch.Tensor, lyr: "FusedLayer") -> torch.Tensor:
         """The spikes a fused layer left in its inter-layer buffer, as the reference's fp32 [T, b, C, h, w] tensor
         (diagnostics / parity tests; the product path never converts)."""
+        if lyr.desc.out_kind == _lib.OUT_LIF8:
+            return stf8_to_nchw(buf, lyr.T, lyr.B, lyr.C_out, lyr.H_out, lyr.W_out)
         return stf_to_nchw(buf, lyr.T, lyr.B, lyr.C_out, lyr.H_out, lyr.W_out)
 
     def run_from_input(self) -> torch.Tensor:

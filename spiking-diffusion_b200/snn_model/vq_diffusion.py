@@ -75,7 +75,10 @@ class DummyModel(engine.PlanCacheMixin, nn.Module):
         self.conv5 = block(512, 256)
         self.conv6 = layer.SpikingSequential(layer.Conv2d(256 + 64, num_embeddings, 3, 1, 1))
         self._plans = {}
-        self.nsplit = 2   # fp16 terms per fp32 weight in the tcgen05 layers (2 = 22-bit weights, 1 = 11-bit)
+        # weight representation of the tcgen05 layers conv2..conv5: 3 = three int8 digits of a 22-bit fixed-point weight
+        # (kind::i8, exact int32 accumulation; default, needs an even T, else falls back to 2), 2 = two fp16 terms
+        # (kind::f16, 22 significant bits), 1 = one fp16 term (11 bits: NOT a parity configuration, experiments only)
+        self.nsplit = 3
 
     def plan(self, b: int, h: int, w: int) -> "engine.DenoiserPlan":
         key = (self.T, b, h, w, self.nsplit) + engine.module_cache_key(self)

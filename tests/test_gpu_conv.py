@@ -334,3 +334,88 @@ def test_tc_multi_pass_layers_carry_the_membrane_state_across_calls(T, B):
             v_got = torch.empty((B, cout, H, H), dtype=torch.float32, device="cuda")
             _lib.check(_lib.lib().sd_state_convert(_lib.ptr(v), _lib.ptr(v_got), B, cout, H, H, 0, _lib.stream_ptr()))
             assert float((v_got.cpu() - v_ref).abs().max()) <= 2e-5
+
+
+# ---- kind::i8 path (nsplit = 3): u8 spikes, three int8 weight digits, exact int32 accumulation ------------------------
+@pytest.mark.parametrize("T,B,C,H,W", [(4, 3, 16, 7, 7), (2, 2, 64, 5, 3), (8, 1, 32, 8, 8)])
+def test_stf8_round_trip(T, B, C, H, W):
+    s = spikes((T, B, C, H, W), 0.3, T + C)
+    buf = engine.stf8_from_nchw(s.cuda())
+    assert buf.dtype == torch.uint8 and buf.numel() == _lib.lib().sd_stf_bytes(T, B, C, H, W)
+    back = engine.stf8_to_nchw(buf, T, B, C, H, W).cpu()
+    assert torch.equal(back, s)
+    vals = set(torch.unique(buf).tolist())
+    assert vals <= {0, 1, 128}
+    assert int((buf == 1).sum()) == int((buf == 128).sum()) == int(s.sum())     # one byte per spike in each plane
+
+
+@pytest.mark.parametrize("cin,cout,B,H,T", [
+    (64, 128, 2, 7, 4), (64, 128, 7, 7, 4), (128, 256, 4, 7, 4), (256, 512, 4, 7, 4), (512, 256, 3, 7, 4),
+    (64, 128, 3, 8, 4), (64, 128, 3, 7, 8), (64, 64, 2, 7, 16), (128, 128, 2, 7, 2), (64, 128, 300, 7, 4),
+    (32, 48, 5, 7, 4), (96, 16, 40, 8, 2),
+])
+def test_tc_int8_conv_bn_lif_matches_oracle(cin, cout, B, H, T):
+    """The same layers as the fp16 test through the int8-digit kernel, to the same bar: spikes bit-exact wherever the
+    oracle's |h - v_th| > 1e-4, flip rate <= 1e-4; the T-sum equals the sum of the written spikes; pad rows stay 0."""
+    seq, p = make_block(cin, cout, seed=cin * 3 + cout + T)
+    fl = tc_layer(seq, T, B, H, _lib.OUT_LIF, 3)
+    assert fl.desc.in_kind == _lib.IN_STF8 and fl.desc.out_kind == _lib.OUT_LIF8 and fl.impl == "tc"
+    s_in = spikes((T, B, cin, H, H), 0.1, B)
+    x8 = engine.stf8_from_nchw(s_in.cuda())
+    out, osum = fl.alloc_out(), fl.alloc_sum()
+    fl.run(x8, out, out_sum=osum)
+    got = engine.stf8_to_nchw(out, T, B, cout, H, H).cpu()
+    assert not bool(torch.isnan(got).any()), "the s and 128*s planes disagree"
+    cur, s_ref, h_ref = oracle_layer(s_in, p, stride=1, padding=1)
+    assert 0.02 < float(s_ref.mean()) < 0.5
+    assert_spikes_match(got, s_ref, h_ref, f"tc-i8 {cin}->{cout} B{B} H{H} T{T}")
+    cnt = engine.stf_to_nchw(osum, 1, B, cout, H, H).cpu()[0]
+    assert torch.equal(cnt, got.sum(0))
+    assert int((out == 1).sum()) == int(got.sum()) and int((out == 128).sum()) == int(got.sum())
+    assert set(torch.unique(out).tolist()) <= {0, 1, 128}
+
+
+def test_tc_int8_matches_fp16_path_and_carries_state():
+    """Same layer through the int8-digit and the two-fp16-term kernels with a caller-owned membrane state over two
+    calls: identical spikes (no near-threshold neuron in this fixture), potentials equal to fp32 rounding."""
+    T, B, H, cin, cout = 4, 6, 7, 128, 256
+    seq, p = make_block(cin, cout, seed=5)
+    a, b = tc_layer(seq, T, B, H, _lib.OUT_LIF, 3), tc_layer(seq, T, B, H, _lib.OUT_LIF, 2)
+    va, vb = a.alloc_state(), b.alloc_state()
+    oa, ob = a.alloc_out(), b.alloc_out()
+    for call in range(2):
+        s_in = spikes((T, B, cin, H, H), 0.1, 9 + call).cuda()
+        a.run(engine.stf8_from_nchw(s_in), oa, v=va)
+        b.run(engine.stf_from_nchw(s_in), ob, v=vb)
+        ga, gb = engine.stf8_to_nchw(oa, T, B, cout, H, H), engine.stf_to_nchw(ob, T, B, cout, H, H)
+        assert float((ga != gb).float().mean()) <= 1e-4
+        assert float((va - vb).abs().max()) <= 1e-4 or float(((va - vb).abs() > 1e-4).float().mean()) <= 1e-4
+
+
+def test_int8_weight_digits_reconstruct_the_weights():
+    """sd_conv_pack_weights_tc (nsplit = 3): 256 * (128 * d0 + d1) + d2, times the returned channel scale, equals the fp32
+    weight to 2^-21 of the channel's largest weight, and the L1 bound that rules out int32 overflow holds."""
+    import ctypes
+    cin, cout, T, B, H = 64, 128, 4, 4, 7
+    seq, p = make_block(cin, cout, seed=11)
+    fl = tc_layer(seq, T, B, H, _lib.OUT_LIF, 3)
+    L = _lib.lib()
+    d = fl.desc
+    w = seq[0].weight.detach().float().contiguous()
+    chan = torch.empty(cout, device="cuda")
+    packed = torch.empty(L.sd_conv_weight_bytes_tc(ctypes.byref(d)), dtype=torch.uint8, device="cuda")
+    _lib.check(L.sd_conv_pack_weights_tc(ctypes.byref(d), w.data_ptr(), packed.data_ptr(), chan.data_ptr(), _lib.stream_ptr()))
+    layout = L.sd_conv_weight_layout_tc(ctypes.byref(d))
+    n_tile, kblk, pair = layout >> 16, (layout >> 4) & 0xFFF, layout & 1
+    halves, chunks = (2 if pair else 1), kblk // 16
+    nh = n_tile // halves
+    main = (cout // n_tile if cout >= n_tile else 1) * (cin // kblk) * 9 * 3 * chunks * n_tile * 16
+    dg = packed[:main].view(torch.int8).reshape(-1, cin // kblk, 9, halves, 3, chunks, nh, 16).cpu().int()
+    wfix = 256 * (128 * dg[:, :, :, :, 0] + dg[:, :, :, :, 1]) + dg[:, :, :, :, 2]       # [nt, kb, tap, hf, chunk, n, 16]
+    # -> [co, ci, tap]
+    wfix = wfix.permute(0, 3, 5, 1, 4, 6, 2).reshape(-1, cin, 9)[:cout]
+    rec = wfix.double() * chan.cpu().double()[:, None, None]
+    wref = w.cpu().reshape(cout, cin, 9).double()
+    err = (rec - wref).abs().amax(dim=(1, 2))
+    assert bool((err <= wref.abs().amax(dim=(1, 2)) * 2.0 ** -21).all())
+    assert int(dg[:, :, :, :, 1].abs().max()) <= 64 and int(wfix.abs().sum(dim=(1, 2)).max()) < 2 ** 31

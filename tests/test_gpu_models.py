@@ -113,7 +113,7 @@ def test_decode_vs_reference_golden_T16():
 def _denoiser_layer_spikes(plan):
     bufs = {"den1": (plan.x1, plan.l1), "den2": (plan.x2, plan.l2), "den3": (plan.x3, plan.l3),
             "den4": (plan.x4, plan.l4), "den5": (plan.x5, plan.l5)}
-    return {k: engine.stf_to_nchw(b, l.T, l.B, l.C_out, l.H_out, l.W_out).cpu() for k, (b, l) in bufs.items()}
+    return {k: plan.spikes_nchw(b, l).cpu() for k, (b, l) in bufs.items()}    # fp16 STF or u8 STF8 buffers
 
 
 def test_denoiser_vs_reference_golden_T16():
@@ -137,7 +137,8 @@ def test_denoiser_vs_reference_golden_T16():
     assert err <= (1e-4 if flips == 0 else 5e-2), err
 
 
-@pytest.mark.parametrize("T,b,K,hw,nsplit", [(4, 8, 128, 7, 2), (4, 5, 128, 8, 2), (8, 4, 512, 7, 2), (4, 8, 128, 7, 1)])
+@pytest.mark.parametrize("T,b,K,hw,nsplit", [(4, 8, 128, 7, 3), (4, 5, 128, 8, 3), (8, 4, 512, 7, 3), (4, 8, 128, 7, 2),
+                                             (4, 5, 128, 8, 2), (8, 4, 512, 7, 2), (4, 8, 128, 7, 1)])
 def test_denoiser_vs_oracle(T, b, K, hw, nsplit):
     m, sd = make_denoiser(T, K, seed=2)
     m.nsplit = nsplit
@@ -154,12 +155,16 @@ def test_denoiser_vs_oracle(T, b, K, hw, nsplit):
         n = f"den{i}"
         near = torch.cummax((O.spike_margin(tr[n][1]) <= SPIKE_MARGIN).to(torch.uint8), dim=0).values.bool()
         diff = got[n] != tr[n][0]
-        if flips == 0 and nsplit == 2:
+        if nsplit >= 2:    # 3 int8 digits (default) or 2 fp16 terms: the parity configurations
             assert int((diff & ~near).sum()) == 0, n
         flips += int(diff.sum()); total += diff.numel()
+        if flips:
+            # a near-threshold neuron moved (tools/diag_i8.py: a few ulps from v_th, equally often on either path): every
+            # later layer sees a different input, so its spikes are no longer comparable with the oracle's
+            break
     rate = flips / total
     # nsplit=1 (11-bit weights) is a reported speed/accuracy knob, NOT the parity configuration: it misses the 1e-4 bar
-    assert rate <= (FLIP_RATE_MAX if nsplit == 2 else 3e-2), rate
+    assert rate <= (FLIP_RATE_MAX if nsplit >= 2 else 3e-2), rate
     if flips == 0:
         assert float((lg - lg_ref).abs().max()) <= 1e-4
 

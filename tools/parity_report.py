@@ -72,8 +72,8 @@ def main():
         lg = m(x.cuda(), t.cuda()).cpu()
         p = m.plan(b, hw, hw)
         bufs = {"den1": (p.x1, p.l1), "den2": (p.x2, p.l2), "den3": (p.x3, p.l3), "den4": (p.x4, p.l4), "den5": (p.x5, p.l5)}
-        got = {k: engine.stf_to_nchw(bf, l.T, l.B, l.C_out, l.H_out, l.W_out).cpu() for k, (bf, l) in bufs.items()}
-        print(f"\n## DummyModel.forward, b={b}, T={T}, K={K}, latent {hw}x{hw}, fp16 weight terms = {nsplit}"
+        got = {k: p.spikes_nchw(bf, l).cpu() for k, (bf, l) in bufs.items()}
+        print(f"\n## DummyModel.forward, b={b}, T={T}, K={K}, latent {hw}x{hw}, weight representation nsplit = {nsplit} (3: int8 digits, 2: fp16 terms)"
               + ("  (NOT the parity configuration)" if nsplit == 1 else ""))
         layer_rows(got, tr, list(bufs))
         print(f"logits max-abs error {float((lg - lg_ref).abs().max()):.3e}, logits abs max {float(lg_ref.abs().max()):.2f}")
