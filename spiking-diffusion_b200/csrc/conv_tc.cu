@@ -53,6 +53,10 @@ constexpr int kTcThreads = 384;
 constexpr int kMaxAStages = 4;
 constexpr int kMaxBStages = 8;
 constexpr uint32_t kSmemBudget = 220 * 1024;
+// shared-memory header: barriers + TMEM slot in the first 1 KB, then two buffers of (scale[256], shift[256]) for the
+// epilogue (the N tile's folded-BN affine, staged while the MMAs of the tile run)
+constexpr uint32_t kHdrBytes = 1024 + 2 * 2 * 256 * 4;
+constexpr uint32_t kVSmemBytes = 256 * 64 * 4;   // membrane potentials of one tile between its passes: [64 columns][256 threads]
 
 struct TcConfig {
   int i8;          // 1: kind::i8 path (nsplit == 3): u8 spikes x three s8 weight digits, two int32 accumulators
@@ -77,6 +81,8 @@ struct TcConfig {
                    //    (needs Wp % 8 == 0).  Measured: no gain, the cost of an MMA does not depend on the alignment
   uint32_t a_stage_bytes, b_stage_bytes, smem_bytes;
   int n_tiles, m_tiles, num_kblocks, c0_blocks;
+  uint32_t v_smem_off;   // != 0: multi-pass tiles keep the membrane potential in shared memory between their passes
+                         // (offset of the [64][256] fp32 block); 0: single pass, T-parallel mode, or no room
 };
 
 struct TcParams {
@@ -307,7 +313,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
   // pair only: "the peer's stage has landed" barriers in the leader, arrived remotely by the peer's relay warp
   auto a_full_peer = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages + 6 + s); };
   auto b_full_peer = [&](int s) { return bar_base + 8u * (3 * kMaxAStages + 2 * kMaxBStages + 6 + s); };
-  const uint32_t a_base = smem_u32(smem + 1024);
+  const uint32_t a_base = smem_u32(smem + kHdrBytes);
+  float* const s_affine = reinterpret_cast<float*>(smem + 1024);     // [2 buffers][scale 256 | shift 256]
+  float* const s_v = c.v_smem_off ? reinterpret_cast<float*>(smem + c.v_smem_off) : nullptr;
   const uint32_t b_base = a_base + c.a_stages * c.a_stage_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -584,8 +592,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
       const int pp = (int)(r % p.P);
       const int py = pp / p.W, px = pp - py * p.W;
       const bool valid = r < p.R_valid;
+      // Stage the N tile's folded-BN affine in shared memory while the MMAs of this tile run (the first pass of a tile
+      // does it; the buffers alternate between tiles, and the named barrier below orders fill -> use).
+      const int tile_par = ((tile - unit0) / unit_stride) & 1;
+      float* const sS = s_affine + tile_par * 512;
+      float* const sH = sS + 256;
+      if (pass == 0) {
+        const int e = threadIdx.x;                    // 256 epilogue threads: one column each (N_TILE <= 256)
+        if (e < c.N_TILE) {
+          const bool in = n0 + e < p.Cout;
+          sS[e] = in ? __ldg(p.scale + n0 + e) : 0.f;
+          sH[e] = in ? __ldg(p.shift + n0 + e) : 0.f;
+        }
+      }
       mbar_wait(acc_full(sc.stage), sc.phase);
       tc_fence_after();
+      if (pass == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
       if (trace && threadIdx.x == 0 && trace_it < 7) trace[3 + trace_it * 8 + 4] = clock64();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc.stage * c.T_acc * ACCS * c.N_TILE);
       // accumulator of local timestep tl, 16 columns from cc: one TMEM load (fp32), or for i8 two (int32 hi and lo)
@@ -608,9 +630,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
         if (n >= p.Cout) continue;  // zero-padded tail of the last N tile
         float sc_[16], sh_[16];
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(p.scale + n + j));
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.shift + n + j));
+        for (int j = 0; j < 16; j += 4) {       // warp-uniform shared-memory reads (broadcast)
+          const float4 a = *reinterpret_cast<const float4*>(sS + cc + j);
+          const float4 b = *reinterpret_cast<const float4*>(sH + cc + j);
           sc_[j] = a.x; sc_[j + 1] = a.y; sc_[j + 2] = a.z; sc_[j + 3] = a.w;
           sh_[j] = b.x; sh_[j + 1] = b.y; sh_[j + 2] = b.z; sh_[j + 3] = b.w;
         }
@@ -644,7 +666,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
           __half2 cnt2[8];   // spike counts so far (exact in fp16: at most T <= 16)
           const bool want_sum = p.out_sum != nullptr;
           const int64_t vrow = ((int64_t)(n >> 3) * p.R_alloc + p.G + r) * 8;  // chunk n/8; next chunk + R_alloc*8
-          if (p.v != nullptr && valid && n < p.Cout && (!first_pass || p.v_load_initial)) {
+          // between the passes of a tile the potential stays in shared memory ([column][thread]: conflict-free); the
+          // state plane in global memory is only read for a caller-provided initial state and written for the caller
+          const bool v_via_smem = s_v != nullptr;
+          float* const sv = s_v + (cc - col_lo) * 256 + (threadIdx.x & 255);     // this thread's 16 columns, stride 256
+          if (v_via_smem && !first_pass) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = sv[j * 256];
+          } else if (p.v != nullptr && valid && n < p.Cout && (!first_pass || p.v_load_initial)) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const float4 a = *reinterpret_cast<const float4*>(p.v + vrow + (int64_t)h * p.R_alloc * 8);
@@ -743,7 +772,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
               *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               *reinterpret_cast<uint4*>(o + p.R_alloc * 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
-            if (p.v != nullptr && (!last_pass || p.v_store_final)) {
+            if (v_via_smem && !last_pass) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) sv[j * 256] = v[j];
+            } else if (p.v != nullptr && (v_via_smem ? p.v_store_final : (!last_pass || p.v_store_final))) {
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 float* o = p.v + vrow + (int64_t)h * p.R_alloc * 8;
@@ -878,10 +910,11 @@ __global__ void __launch_bounds__(256) lif_from_currents_kernel(const TcParams p
 //   SD_TC_NTILE, SD_TC_KBLK, SD_TC_ACC_STAGES, SD_TC_ALIGN   tile shape overrides
 //   SD_TC_PERSIST=0         one work unit per CTA / cluster
 //   SD_TC_TPAR=0            no T-parallel small-batch mode
+//   SD_TC_VSMEM=0           multi-pass tiles carry the membrane potential through the L2 state plane instead of smem
 //   SD_TC_DBG (-DSD_TRACE build only, with sd_debug_tc_trace)   1: skip spike stores, 2: skip TMEM loads, 4: un-masked
 //                           MMAs in the single-CTA kernel (timing experiments only; 4 gives wrong results at borders)
 struct TcKnobs {
-  int pair, small_batch_split, tchunk, tacc, wide256, n256, ntile, kblk, acc_stages, align, persist, tpar, dbg;
+  int pair, small_batch_split, tchunk, tacc, wide256, n256, ntile, kblk, acc_stages, align, persist, tpar, dbg, v_smem;
 };
 static TcKnobs g_knobs;
 static std::once_flag g_knobs_once;
@@ -904,6 +937,7 @@ static void load_knobs() {
   k.persist = env_int("SD_TC_PERSIST", 1);
   k.tpar = env_int("SD_TC_TPAR", 1);
   k.dbg = env_int("SD_TC_DBG", 0);
+  k.v_smem = env_int("SD_TC_VSMEM", 1);
   g_knobs = k;
 }
 static const TcKnobs& knobs() {
@@ -976,17 +1010,25 @@ static int tc_config_i8(const sd_conv_desc* d, TcConfig* c) {
     c->a_stage_bytes = (uint32_t)c->T_acc * 2 * (kblk / 16) * c->rows_ld * 16;
     c->b_stage_bytes = 3u * (kblk / 16) * (c->pair ? n_tile / 2 : n_tile) * 16;   // per CTA
     const uint32_t b_ref = 3u * (kblk / 16) * 128 * 16;      // batch-independent fit test (see the fp16 path)
-    if (2 * c->a_stage_bytes + 4 * b_ref + 1024 > kSmemBudget) continue;
+    if (2 * c->a_stage_bytes + 4 * b_ref + kHdrBytes > kSmemBudget) continue;
     c->KBLK = kblk;
     found = true;
   }
   if (!found) { set_error("conv_tc(i8): no K block fits shared memory"); return SD_ERR_UNSUPPORTED; }
-  c->a_stages = (int)((kSmemBudget - 1024 - 4 * c->b_stage_bytes) / c->a_stage_bytes);
-  if (c->a_stages > 3) c->a_stages = 3;
-  const uint32_t left = kSmemBudget - 1024 - c->a_stages * c->a_stage_bytes;
+  // multi-pass tiles keep the membrane potential in shared memory between their passes when that still leaves
+  // >= 2 A stages and >= 4 B stages (else it travels through the L2-resident state plane, as in T-parallel mode)
+  uint32_t v_smem = (c->n_tchunks > 1 && !c->tpar && knobs().v_smem) ? kVSmemBytes : 0;
+  for (;;) {
+    c->a_stages = (int)(((int64_t)kSmemBudget - kHdrBytes - v_smem - 4 * (int64_t)c->b_stage_bytes) / c->a_stage_bytes);
+    if (c->a_stages > 3) c->a_stages = 3;
+    if (c->a_stages >= 2 || v_smem == 0) break;
+    v_smem = 0;
+  }
+  const uint32_t left = kSmemBudget - kHdrBytes - v_smem - c->a_stages * c->a_stage_bytes;
   c->b_stages = (int)(left / c->b_stage_bytes);
   if (c->b_stages > kMaxBStages) c->b_stages = kMaxBStages;
-  c->smem_bytes = 1024 + c->a_stages * c->a_stage_bytes + c->b_stages * c->b_stage_bytes;
+  c->v_smem_off = v_smem ? kHdrBytes + c->a_stages * c->a_stage_bytes + c->b_stages * c->b_stage_bytes : 0;
+  c->smem_bytes = kHdrBytes + c->a_stages * c->a_stage_bytes + c->b_stages * c->b_stage_bytes + v_smem;
   if (c->smem_bytes < 117u * 1024u) c->smem_bytes = 117u * 1024u;
   c->n_tiles = (d->C_out + n_tile - 1) / n_tile;
   c->m_tiles = m_tiles;
@@ -1092,7 +1134,7 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
       // on the batch size: the fit test uses the N = 128 stage size even when a small batch runs narrower tiles.
       // A batch shard then reproduces the unsharded result bit for bit.
       const uint32_t b_ref = (uint32_t)d->nsplit * (kblk / 8) * (n_tile > 128 ? n_tile : 128) * 16;
-      if (2 * c->a_stage_bytes + 4 * b_ref + 1024 > kSmemBudget) continue;
+      if (2 * c->a_stage_bytes + 4 * b_ref + kHdrBytes > kSmemBudget) continue;
       c->KBLK = kblk;
       found = true;
     }
@@ -1100,13 +1142,19 @@ static int tc_config(const sd_conv_desc* d, TcConfig* c) {
   if (!found) { set_error("conv_tc: no K block fits shared memory"); return SD_ERR_UNSUPPORTED; }
   const int kblk = c->KBLK;
   // A ring first (2..4 K blocks in flight), the rest of the budget to the B ring (one tap per stage)
-  c->a_stages = (int)((kSmemBudget - 1024 - 4 * c->b_stage_bytes) / c->a_stage_bytes);
-  if (c->a_stages > kMaxAStages) c->a_stages = kMaxAStages;
-  if (c->a_stages > 3) c->a_stages = 3;
-  uint32_t left = kSmemBudget - 1024 - c->a_stages * c->a_stage_bytes;
+  uint32_t v_smem = (c->n_tchunks > 1 && !c->tpar && n_tile <= 128 && knobs().v_smem) ? kVSmemBytes : 0;
+  for (;;) {
+    c->a_stages = (int)(((int64_t)kSmemBudget - kHdrBytes - v_smem - 4 * (int64_t)c->b_stage_bytes) / c->a_stage_bytes);
+    if (c->a_stages > kMaxAStages) c->a_stages = kMaxAStages;
+    if (c->a_stages > 3) c->a_stages = 3;
+    if (c->a_stages >= 2 || v_smem == 0) break;
+    v_smem = 0;
+  }
+  uint32_t left = kSmemBudget - kHdrBytes - v_smem - c->a_stages * c->a_stage_bytes;
   c->b_stages = (int)(left / c->b_stage_bytes);
   if (c->b_stages > kMaxBStages) c->b_stages = kMaxBStages;
-  c->smem_bytes = 1024 + c->a_stages * c->a_stage_bytes + c->b_stages * c->b_stage_bytes;
+  c->v_smem_off = v_smem ? kHdrBytes + c->a_stages * c->a_stage_bytes + c->b_stages * c->b_stage_bytes : 0;
+  c->smem_bytes = kHdrBytes + c->a_stages * c->a_stage_bytes + c->b_stages * c->b_stage_bytes + v_smem;
   // every CTA allocates all 512 TMEM columns: ask for more than half of the SM's shared memory so that two CTAs of
   // this kernel are never co-resident (the second would only sit in tcgen05.alloc until the first one exits)
   if (c->smem_bytes < 117u * 1024u) c->smem_bytes = 117u * 1024u;
@@ -1288,7 +1336,7 @@ int sd_conv_tc_supported(const sd_conv_desc* d) {
 int64_t sd_conv_workspace_bytes(const sd_conv_desc* d) {
   TcConfig c;
   if (!d || validate_conv_desc(d) != SD_OK || tc_config(d, &c) != SD_OK) return 0;
-  if (c.n_tchunks <= 1) return 0;
+  if (c.n_tchunks <= 1 || (!c.tpar && c.v_smem_off != 0)) return 0;   // potential carried in shared memory
   // one fp32 state plane [C_out/8][R_alloc][8]; in T-parallel mode one plane of currents per timestep instead
   const int64_t plane = (int64_t)c8(d->C_out) * stf_rows(d->B, d->H_out, d->W_out) * 8 * (int64_t)sizeof(float);
   return c.tpar ? plane * d->T : plane;
@@ -1366,7 +1414,7 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
     p.cur = (float*)a->workspace;
     p.v = a->v;
   }
-  if (c.n_tchunks > 1 && !c.tpar && p.v == nullptr) {
+  if (c.n_tchunks > 1 && !c.tpar && p.v == nullptr && c.v_smem_off == 0) {
     set_error("conv_tc: T=%d runs as %d passes and needs args.v or args.workspace (sd_conv_workspace_bytes)", d->T,
               c.n_tchunks);
     return SD_ERR_INVALID;

@@ -1,5 +1,5 @@
 """Cycle-stamp trace of the tcgen05 conv kernel's MMA and epilogue warps per layer (GPU box).
-Usage: python tools/trace_tc.py [workload] [sub_batch]   -> where a tile's time goes: operand stalls, MMA, epilogue, hand-off."""
+Usage: python tools/trace_tc.py [workload] [sub_batch] [nsplit]   -> where a tile's time goes: operand stalls, MMA, epilogue, hand-off."""
 import os
 import sys
 
@@ -24,7 +24,9 @@ def main():
     dev = torch.device("cuda", 0)
     vae, den, ab, _, _ = bench.build_models(wl, dev)
     T, hw = wl["T"], wl["hw"]
-    dp = engine.DenoiserPlan(den, T, b, hw, hw, nsplit=2)
+    nsplit = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    dp = engine.DenoiserPlan(den, T, b, hw, hw, nsplit=nsplit)
+    print(f"# workload {sys.argv[1] if len(sys.argv) > 1 else 'cfg2'}, b={b}, nsplit={nsplit} ({dp.l4.mma_kind()})")
     x_t = torch.full((b * hw * hw,), wl["K"], dtype=torch.int64, device=dev)
     x_t[::3] = 5
     for _ in range(3):
