@@ -303,6 +303,39 @@ int sd_denoiser_input(const int64_t* x_t, float* out, int B, int H, int W, int t
 /* clip(pred + 0.5, 0, 1) * 255 -> uint8 (R/main.py:401). */
 int sd_to_uint8(const float* pred, uint8_t* out, int64_t N, void* stream);
 
+/* ---- (f.4) quality metrics on given features (the step after the path) -----------
+ * The algebra of the reference's evaluation block that needs no pretrained network.  workspace: device memory of
+ * sd_metric_workspace_bytes(n_elements, d, m) bytes (pass the sizes of the call: d for the Frechet distance, m for the
+ * MMD, K + N / splits as n_elements for the inception score, 0 otherwise).  Scalars are written to DEVICE memory.
+ *   sd_metric_mse            F.mse_loss(a, b)                                            R/main.py:319
+ *   sd_metric_ssim           metric.pytorch_ssim.SSIM(window_size)(img1, img2): gaussian window (sigma 1.5), zero padding,
+ *                            C1 = 0.01^2, C2 = 0.03^2, mean of the SSIM map; window_host = the window_size^2 fp32 window
+ *                            (create_window); per_plane_sum_or_null [N*C] gets the per-plane sums (size_average=False)
+ *                                                                R/metric/pytorch_ssim/__init__.py:7-37, R/main.py:320-321
+ *   sd_metric_feature_stats  mu = mean(act, 0), sigma = np.cov(act, rowvar=False) in fp64; act fp32 or fp64 [N, d]
+ *                                                                                        R/metric/Fid_score.py:100-113
+ *   sd_metric_frechet        |mu1-mu2|^2 + tr(s1) + tr(s2) - 2 tr(U sqrt(S) Vh), U S Vh = svd(s1 s2): the reference's own
+ *                            sqrtm (an SVD, not scipy's), by a one-sided Jacobi SVD in fp64.  Blocks the stream (sweeps are
+ *                            repeated until none rotates).                         R/metric/Fid_score.py:14-17,116-173
+ *   sd_metric_poly_mmd2      unbiased MMD^2 with k(x, y) = (gamma x.y + coef)^degree on fp32 features [m, d] of both sets:
+ *                            (sum_{i!=j} k_xx + sum_{i!=j} k_yy) / (m (m-1)) - 2 sum k_xy / m^2 -- the estimator of
+ *                            torchmetrics.image.kid (poly_mmd), which R/main.py:465-490 calls; torchmetrics is not part of
+ *                            the reference tree and no version is pinned there
+ *   sd_metric_inception_score  per split exp(mean_i KL(p_i || mean_i p_i)) with scipy.stats.entropy's normalisation, then
+ *                            mean and population std over the splits; preds fp64 [N, K]        R/metric/IS_score.py:58-72
+ */
+int64_t sd_metric_workspace_bytes(int64_t n_elements, int d, int m);
+int sd_metric_mse(const float* a, const float* b, int64_t n, float* out_dev, void* workspace, void* stream);
+int sd_metric_ssim(const float* img1, const float* img2, int N, int C, int H, int W, int window_size,
+                   const float* window_host, float* out_dev, float* per_plane_sum_or_null, void* workspace, void* stream);
+int sd_metric_feature_stats(const void* act, int act_is_f64, int64_t N, int d, double* mu_out, double* sigma_out, void* stream);
+int sd_metric_frechet(const double* mu1, const double* sigma1, const double* mu2, const double* sigma2, int d,
+                      double* out_dev, int* sweeps_out, void* workspace, void* stream);
+int sd_metric_poly_mmd2(const float* fx, const float* fy, int m, int d, int degree, double gamma, double coef,
+                        double* out_dev, void* workspace, void* stream);
+int sd_metric_inception_score(const double* preds, int64_t N, int K, int splits, double* mean_out_dev, double* std_out_dev,
+                              void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

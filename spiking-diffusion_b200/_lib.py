@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libsd_b200.so")
-SOURCES = ["lif.cu", "vq.cu", "conv_simt.cu", "conv_tc.cu", "sample.cu", "train.cu"]
+SOURCES = ["lif.cu", "vq.cu", "conv_simt.cu", "conv_tc.cu", "sample.cu", "train.cu", "metrics.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--extended-lambda",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 
@@ -28,6 +28,8 @@ SYMBOLS = [
     "sd_conv_pack_weights_tc", "sd_conv_lif_simt", "sd_conv_lif_tc", "sd_conv_tc_supported", "sd_debug_tc_trace", "sd_debug_tc_reload_knobs", "sd_conv_wgrad_workspace_bytes", "sd_conv_wgrad",
     "sd_bn_train_forward", "sd_bn_backward", "sd_bn_local_stats", "sd_bn_backward_reduce", "sd_bn_backward_apply", "sd_philox_uniform",
     "sd_philox_exponential", "sd_philox_offset_increment", "sd_sample_step", "sd_sample_step_dev", "sd_denoiser_input", "sd_to_uint8",
+    "sd_metric_workspace_bytes", "sd_metric_mse", "sd_metric_ssim", "sd_metric_feature_stats", "sd_metric_frechet",
+    "sd_metric_poly_mmd2", "sd_metric_inception_score",
 ]
 
 
@@ -162,6 +164,13 @@ def _declare(lib: ctypes.CDLL) -> None:
         "sd_sample_step_dev": (i, [vp, vp, vp, vp, i64, i, i, f, vp, u64, u64, i64, i64, vp]),
         "sd_denoiser_input": (i, [vp, vp, i, i, i, i, vp]),
         "sd_to_uint8": (i, [vp, vp, i64, vp]),
+        "sd_metric_workspace_bytes": (i64, [i64, i, i]),
+        "sd_metric_mse": (i, [vp, vp, i64, vp, vp, vp]),
+        "sd_metric_ssim": (i, [vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp]),
+        "sd_metric_feature_stats": (i, [vp, i, i64, i, vp, vp, vp]),
+        "sd_metric_frechet": (i, [vp, vp, vp, vp, i, vp, ctypes.POINTER(i), vp, vp]),
+        "sd_metric_poly_mmd2": (i, [vp, vp, i, i, i, ctypes.c_double, ctypes.c_double, vp, vp, vp]),
+        "sd_metric_inception_score": (i, [vp, i64, i, i, vp, vp, vp, vp]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
