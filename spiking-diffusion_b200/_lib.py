@@ -75,7 +75,9 @@ def _build_to(lib_path: str, obj_dir: str, extra_flags, verbose: bool) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        # SD_NVCC_EXTRA: experiment macros for the diagnostics build (e.g. "-DSD_TC_SINGLE_BUF"), never for the shipped one
+        more = os.environ.get("SD_NVCC_EXTRA", "").split() if extra_flags else []
+        cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + more + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:

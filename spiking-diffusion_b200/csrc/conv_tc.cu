@@ -50,6 +50,8 @@
 namespace sd {
 
 constexpr int kTcThreads = 384;
+constexpr int kRegsOther = 128;        // warps 8-11 after setmaxnreg.dec
+constexpr int kRegsEpilogue = 192;    // warps 0-7 after setmaxnreg.inc: 256 * 216 + 128 * 72 = 64512 <= 65536
 constexpr int kMaxAStages = 4;
 constexpr int kMaxBStages = 8;
 constexpr uint32_t kSmemBudget = 220 * 1024;
@@ -370,6 +372,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
   const int planes_t = I8 ? 2 * chunks : chunks * c.ndx;   // planes per timestep in an A stage
   const uint32_t plane_bytes = (uint32_t)c.rows_ld * 16u;
 
+  // Register budget by role (setmaxnreg works on aligned groups of four warps): the producer / MMA / relay warps of the
+  // third warpgroup need few registers and give theirs up; the two epilogue warpgroups take them, so the LIF epilogue
+  // (16 columns x 2 timesteps in flight, affine, potentials) is no longer scheduled against the 168-register ceiling.
+#ifdef SD_TC_SETMAXNREG
+  if (warp >= 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue));
+#endif
+
   if (warp == 8) {
     // ===== A producer =====
     PipeState st;
@@ -685,6 +695,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = p.hard_reset ? p.v_reset : 0.f;
           }
+          uint32_t cnt8[4] = {0u, 0u, 0u, 0u};   // i8 path: this pass's counts, one byte per column
 #pragma unroll
           for (int k = 0; k < 8; ++k) cnt2[k] = __floats2half2_rn(0.f, 0.f);
           if (!first_pass && want_sum && valid) {   // spike counts of the earlier passes
@@ -697,47 +708,63 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
               for (int k = 0; k < 4; ++k) cnt2[4 * h + k] = h2[k];
             }
           }
-          // one timestep of 16 columns: BN affine, charge, fire, reset; spikes leave as packed fp16
+          // One timestep of 16 columns: BN affine, charge, fire, reset.  The spike is kept as an all-ones / zero mask:
+          // the hard reset to 0 is h AND NOT mask (exactly s ? 0 : h) and one LOP3 per spike drops its bit pattern into
+          // the packed output word (fp16 1.0 = 0x3C00 per half, or 0x01 per byte for the u8 format).
           auto lif_step = [&](auto fast_tag, const uint32_t (&acc)[16], int tl) {
             constexpr bool kFast = decltype(fast_tag)::value;
-            uint32_t packed[8];
+            constexpr int kWords = I8 ? 4 : 8;
+            uint32_t packed[kWords];
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              float sf[2];
+            for (int k = 0; k < kWords; ++k) packed[k] = 0u;
 #pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const float x = fmaf(__uint_as_float(acc[j + u]), sc_[j + u], sh_[j + u]);
-                if constexpr (kFast) {
-                  // hard reset to 0, tau a power of two: h = v + (x - v) * (1/tau) is one exact-product FMA, and
-                  // v' = h - h * s is exactly (s ? 0 : h)
-                  const float h = fmaf(__fsub_rn(x, v[j + u]), inv_tau, v[j + u]);
-                  sf[u] = h >= p.v_th ? 1.f : 0.f;
-                  v[j + u] = fmaf(-h, sf[u], h);
-                } else {
-                  const float dv = p.hard_reset ? __fsub_rn(x, __fsub_rn(v[j + u], p.v_reset)) : __fsub_rn(x, v[j + u]);
-                  const float h = __fadd_rn(v[j + u], tau_pow2 ? __fmul_rn(dv, inv_tau) : __fdiv_rn(dv, p.tau));
-                  const bool s = h >= p.v_th;
-                  sf[u] = s ? 1.f : 0.f;
-                  v[j + u] = p.hard_reset ? (s ? p.v_reset : h) : (s ? __fsub_rn(h, p.v_th) : h);
-                }
+            for (int j = 0; j < 16; ++j) {
+              const float x = fmaf(__uint_as_float(acc[j]), sc_[j], sh_[j]);
+              uint32_t m;
+              if constexpr (kFast) {
+                // hard reset to 0, tau a power of two: h = v + (x - v) * (1/tau) is one exact-product FMA
+                // (inline PTX: one predicate per neuron-timestep drives the reset select and a predicated OR of the spike's
+                // bit pattern into the packed output word -- 3 instructions; left to itself the compiler spends 4-5)
+                const float h = fmaf(__fsub_rn(x, v[j]), inv_tau, v[j]);
+                const uint32_t pat = I8 ? (1u << (8 * (j & 3))) : (0x3C00u << (16 * (j & 1)));
+                asm("{\n\t"
+                    ".reg .pred q;\n\t"
+                    "setp.ge.f32 q, %2, %3;\n\t"
+                    "selp.f32 %0, 0f00000000, %2, q;\n\t"
+                    "@q or.b32 %1, %1, %4;\n\t"
+                    "}"
+                    : "=f"(v[j]), "+r"(packed[I8 ? (j >> 2) : (j >> 1)])
+                    : "f"(h), "f"(p.v_th), "r"(pat));
+                m = 0u;
+              } else {
+                const float dv = p.hard_reset ? __fsub_rn(x, __fsub_rn(v[j], p.v_reset)) : __fsub_rn(x, v[j]);
+                const float h = __fadd_rn(v[j], tau_pow2 ? __fmul_rn(dv, inv_tau) : __fdiv_rn(dv, p.tau));
+                const bool s_ = h >= p.v_th;
+                m = s_ ? 0xFFFFFFFFu : 0u;
+                v[j] = p.hard_reset ? (s_ ? p.v_reset : h) : (s_ ? __fsub_rn(h, p.v_th) : h);
               }
-              const __half2 s2 = __floats2half2_rn(sf[0], sf[1]);
-              packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&s2);
-              if (want_sum) cnt2[j >> 1] = __hadd2(cnt2[j >> 1], s2);
+              if constexpr (!kFast) {
+                if constexpr (I8) packed[j >> 2] |= m & (1u << (8 * (j & 3)));
+                else packed[j >> 1] |= m & (0x3C00u << (16 * (j & 1)));
+              }
+            }
+            if (want_sum) {
+              if constexpr (I8) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) cnt8[k] += packed[k];     // four byte counters per word (at most T <= 16)
+              } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) cnt2[k] = __hadd2(cnt2[k], *reinterpret_cast<const __half2*>(&packed[k]));
+              }
             }
             if constexpr (I8) {
               if (valid && n < p.Cout && p.out_spk8 != nullptr) {
-                // fp16 {0, 1.0} pairs -> bytes {0, 1}: bit 10 of each half is the spike; one 16-byte row = 16 channels.
-                // The 128*s plane of the same timestep lies Cout/16 planes further.
-                uint32_t w8[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  w8[k] = __byte_perm((packed[2 * k] >> 10) & 0x00010001u, (packed[2 * k + 1] >> 10) & 0x00010001u, 0x6420);
+                // one 16-byte row = 16 channels; the 128*s plane of the same timestep lies Cout/16 planes further
                 const int t = tch * c.T_acc + tl;
                 const int64_t plane = (int64_t)(p.Cout8 >> 1) * p.R_alloc * 16;
                 uint8_t* o = p.out_spk8 + (int64_t)(t * 2) * plane + (((int64_t)(n >> 4)) * p.R_alloc + p.G + r) * 16;
-                *reinterpret_cast<uint4*>(o) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
-                *reinterpret_cast<uint4*>(o + plane) = make_uint4(w8[0] << 7, w8[1] << 7, w8[2] << 7, w8[3] << 7);
+                *reinterpret_cast<uint4*>(o) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                *reinterpret_cast<uint4*>(o + plane) = make_uint4(packed[0] << 7, packed[1] << 7, packed[2] << 7, packed[3] << 7);
               }
             } else if (valid && n < p.Cout && p.out_spk != nullptr && !(dbg & 1)) {
               const int t = tch * c.T_acc + tl;
@@ -748,6 +775,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
           };
           // two register sets: the TMEM load of timestep t + 1 is in flight while timestep t is computed
           auto lif_all = [&](auto fast_tag) {
+#ifdef SD_TC_SINGLE_BUF
+            if constexpr (I8) {
+              uint32_t accA[16], loA[16];
+              for (int tl = 0; tl < c.T_acc; ++tl) {
+                ld_acc(tl, cc, accA, loA);
+                conv_value(accA, loA);
+                lif_step(fast_tag, accA, tl);
+              }
+              return;
+            }
+#endif
             uint32_t accA[16], accB[16], loA[16], loB[16];
             const bool ld = !(dbg & 2);
 #pragma unroll
@@ -764,9 +802,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
               }
             }
           };
+          if (trace && threadIdx.x == 0 && trace_it < 7 && cc == col_lo) trace[3 + trace_it * 8 + 6] = clock64();   // state loaded
           if (fast_lif) lif_all(std::true_type{}); else lif_all(std::false_type{});
+          if (trace && threadIdx.x == 0 && trace_it < 7 && cc == col_lo) trace[3 + trace_it * 8 + 7] = clock64();   // LIF of group 0 done
           if (valid && n < p.Cout) {
             if (want_sum) {
+              if constexpr (I8) {   // byte counters of this pass -> fp16, added to the earlier passes' counts (exact)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  const uint32_t w = cnt8[k >> 1] >> (16 * (k & 1));
+                  cnt2[k] = __hadd2(cnt2[k], __halves2half2(__ushort2half_rn((unsigned short)(w & 0xFFu)),
+                                                            __ushort2half_rn((unsigned short)((w >> 8) & 0xFFu))));
+                }
+              }
               const uint32_t* pk = reinterpret_cast<const uint32_t*>(cnt2);
               __half* o = p.out_sum + ((int64_t)(n >> 3) * p.R_alloc + p.G + r) * 8;
               *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);

@@ -72,6 +72,10 @@ def main():
                     msg += f"hand-off epi release -> mma start {int(np.median(t[:, base + 0] - t[:, pb + 5]))}; "
             t = tr[e]
             msg += f"epilogue {int(np.median(t[:, base + 5] - t[:, base + 4]))} (max {int((t[:, base + 5] - t[:, base + 4]).max())}) on {int(e.sum())} CTAs"
+            g = t[t[:, base + 7] != 0]
+            if len(g):   # LIF layers: first 16-column group of warp 0
+                msg += (f"; group 0: state loaded after {int(np.median(g[:, base + 6] - g[:, base + 4]))}, "
+                        f"LIF over the pass's timesteps {int(np.median(g[:, base + 7] - g[:, base + 6]))}")
             print(msg)
         # tail: last epilogue release -> exit
         last = np.zeros(len(tr), dtype=np.int64)
