@@ -615,6 +615,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
           sH[e] = in ? __ldg(p.shift + n0 + e) : 0.f;
         }
       }
+      asm volatile("" ::"r"(n0), "r"(pp), "r"(py), "r"(px));   // keep the tile's index arithmetic (divisions) above the wait
       mbar_wait(acc_full(sc.stage), sc.phase);
       tc_fence_after();
       if (pass == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -775,8 +776,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
           };
           // two register sets: the TMEM load of timestep t + 1 is in flight while timestep t is computed
           auto lif_all = [&](auto fast_tag) {
-#ifdef SD_TC_SINGLE_BUF
             if constexpr (I8) {
+              // one register set: with hi + lo per timestep a second set pushes the epilogue to the 168-register ceiling
+              // and the scheduler loses more to the serialised code than the TMEM load latency costs (cycle-stamp
+              // trace: 9.5 k -> 8.1 k cycles per pass)
               uint32_t accA[16], loA[16];
               for (int tl = 0; tl < c.T_acc; ++tl) {
                 ld_acc(tl, cc, accA, loA);
@@ -785,7 +788,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
               }
               return;
             }
-#endif
             uint32_t accA[16], accB[16], loA[16], loB[16];
             const bool ld = !(dbg & 2);
 #pragma unroll
