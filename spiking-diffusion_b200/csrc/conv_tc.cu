@@ -49,7 +49,13 @@
 
 namespace sd {
 
-constexpr int kTcThreads = 384;
+#ifndef SD_TC_EPI_WARPS
+#define SD_TC_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = SD_TC_EPI_WARPS;          // epilogue warps: 8 or 12 (each TMEM lane quarter is served by kEpiWarps / 4)
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kTcThreads = kEpiThreads + 128;       // + A producer, B producer, MMA issuer, TMEM allocator / relay
+constexpr int kWarpA = kEpiWarps, kWarpB = kEpiWarps + 1, kWarpMma = kEpiWarps + 2, kWarpAux = kEpiWarps + 3;
 constexpr int kRegsOther = 128;        // warps 8-11 after setmaxnreg.dec
 constexpr int kRegsEpilogue = 192;    // warps 0-7 after setmaxnreg.inc: 256 * 216 + 128 * 72 = 64512 <= 65536
 constexpr int kMaxAStages = 4;
@@ -58,7 +64,8 @@ constexpr uint32_t kSmemBudget = 220 * 1024;
 // shared-memory header: barriers + TMEM slot in the first 1 KB, then two buffers of (scale[256], shift[256]) for the
 // epilogue (the N tile's folded-BN affine, staged while the MMAs of the tile run)
 constexpr uint32_t kHdrBytes = 1024 + 2 * 2 * 256 * 4;
-constexpr uint32_t kVSmemBytes = 256 * 64 * 4;   // membrane potentials of one tile between its passes: [64 columns][256 threads]
+constexpr int kMaxColsPerThread = 16 * ((8 + kEpiWarps / 4 - 1) / (kEpiWarps / 4));   // N = 128: 64 (8 warps) / 48 (12 warps)
+constexpr uint32_t kVSmemBytes = kEpiThreads * kMaxColsPerThread * 4;   // potentials of one tile between its passes: [columns][threads]
 
 struct TcConfig {
   int i8;          // 1: kind::i8 path (nsplit == 3): u8 spikes x three s8 weight digits, two int32 accumulators
@@ -336,10 +343,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
   if (threadIdx.x == 0) {
     for (int s = 0; s < c.a_stages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); mbar_init(a_full_peer(s), 1); }
     for (int s = 0; s < c.b_stages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); mbar_init(b_full_peer(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), PAIR ? 16 : 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), PAIR ? 2 * kEpiWarps : kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 11) {
+  if (warp == kWarpAux) {
     if (PAIR) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                    "r"(512u));
@@ -380,7 +387,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
   else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue));
 #endif
 
-  if (warp == 8) {
+  if (warp == kWarpA) {
     // ===== A producer =====
     PipeState st;
     const int ncopy = c.T_acc * planes_t;
@@ -420,7 +427,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
         st.advance(c.a_stages);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kWarpB) {
     // ===== B producer (whole warp converged; one elected lane issues) =====
     PipeState st;
     const int64_t stage_halfs = c.b_stage_bytes / 2;
@@ -441,7 +448,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
         st.advance(c.b_stages);
       }
     }
-  } else if (PAIR && warp == 11 && !leader) {
+  } else if (PAIR && warp == kWarpAux && !leader) {
     // ===== relay (peer CTA): tell the leader's MMA warp when this CTA's stages have landed, in consumption order =====
     PipeState sa, sb;
     for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
@@ -458,7 +465,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
         sa.advance(c.a_stages);
       }
     }
-  } else if (warp == 10 && leader) {
+  } else if (warp == kWarpMma && leader) {
     // ===== MMA issuer (whole warp converged; one elected lane issues tcgen05.mma / tcgen05.commit) =====
     PipeState sa, sb, sc;
     // descriptor words: lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version(1)<<14; all stepping is done on lo
@@ -580,12 +587,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
       ++trace_it;
       sc.advance(c.acc_stages);
     }
-  } else if (warp < 8) {
+  } else if (warp < kEpiWarps) {
     // ===== epilogue =====
     PipeState sc;
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int col_lo = (warp >> 2) * (c.N_TILE >> 1);
-    const int col_hi = col_lo + (c.N_TILE >> 1);
+    // the kEpiWarps / 4 warps of a lane quarter share the tile's 16-column groups
+    constexpr int kParts = kEpiWarps / 4;
+    const int n_groups = c.N_TILE >> 4;
+    const int col_lo = 16 * ((n_groups * (warp >> 2)) / kParts);
+    const int col_hi = 16 * ((n_groups * ((warp >> 2) + 1)) / kParts);
     const float inv_T = 1.0f / (float)p.T;
     // x / tau == x * (1/tau) bit for bit when tau is a power of two (the reference uses tau = 2)
     int tau_exp;
@@ -618,7 +628,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
       asm volatile("" ::"r"(n0), "r"(pp), "r"(py), "r"(px));   // keep the tile's index arithmetic (divisions) above the wait
       mbar_wait(acc_full(sc.stage), sc.phase);
       tc_fence_after();
-      if (pass == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (pass == 0) asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       if (trace && threadIdx.x == 0 && trace_it < 7) trace[3 + trace_it * 8 + 4] = clock64();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc.stage * c.T_acc * ACCS * c.N_TILE);
       // accumulator of local timestep tl, 16 columns from cc: one TMEM load (fp32), or for i8 two (int32 hi and lo)
@@ -680,10 +690,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
           // between the passes of a tile the potential stays in shared memory ([column][thread]: conflict-free); the
           // state plane in global memory is only read for a caller-provided initial state and written for the caller
           const bool v_via_smem = s_v != nullptr;
-          float* const sv = s_v + (cc - col_lo) * 256 + (threadIdx.x & 255);     // this thread's 16 columns, stride 256
+          float* const sv = s_v + (cc - col_lo) * kEpiThreads + threadIdx.x;     // this thread's 16 columns, stride kEpiThreads
           if (v_via_smem && !first_pass) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = sv[j * 256];
+            for (int j = 0; j < 16; ++j) v[j] = sv[j * kEpiThreads];
           } else if (p.v != nullptr && valid && n < p.Cout && (!first_pass || p.v_load_initial)) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -824,7 +834,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
             }
             if (v_via_smem && !last_pass) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) sv[j * 256] = v[j];
+              for (int j = 0; j < 16; ++j) sv[j * kEpiThreads] = v[j];
             } else if (p.v != nullptr && (v_via_smem ? p.v_store_final : (!last_pass || p.v_store_final))) {
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
@@ -867,7 +877,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();
   if (trace && threadIdx.x == 0) trace[2] = clock64();
-  if (warp == 11) {
+  if (warp == kWarpAux) {
     tc_fence_after();
     if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
