@@ -148,8 +148,11 @@ enum {
   SD_IN_REAL_CONST = 0, /* fp32 [B, C_in, H_in, W_in], identical at every timestep (R/main.py:133 repeat) */
   SD_IN_REAL_SEQ = 1,   /* fp32 [T, B, C_in, H_in, W_in] */
   SD_IN_STF = 2,        /* fp16 STF spikes (or T-summed spike counts when in_T == 1) */
-  SD_IN_STF8 = 3        /* u8 STF8 spikes: [T][2][C/16][R_alloc][16], per timestep the planes of s in {0,1} and of
+  SD_IN_STF8 = 3,       /* u8 STF8 spikes: [T][2][C/16][R_alloc][16], per timestep the planes of s in {0,1} and of
                            128*s in {0,128}; operand of the kind::i8 layers (sd_conv_lif_tc with nsplit = 3) */
+  SD_IN_TOKENS = 4      /* the denoiser's input built on the fly: args.in = int64 token ids [B, H_in, W_in], channel 0 =
+                           (float)token, channel 1 = args.in_scalar (the diffusion time t), identical at every timestep:
+                           cat(x, t * ones) -> repeat(T) of R/snn_model/vq_diffusion.py:195-198.  C_in must be 2. */
 };
 enum {
   SD_OUT_LIF = 0,       /* BN affine -> LIF over T -> spikes (STF) [+ optional T-sum STF] */
@@ -195,6 +198,7 @@ typedef struct sd_conv_args {
   const float* memout_coef_host; /* SD_OUT_MEMOUT_TANH: HOST pointer, T floats (the `memout.coef` buffer) */
   void* workspace;       /* tc only: scratch of sd_conv_workspace_bytes(desc) bytes (0 for T <= 4), or NULL; used to
                             carry the membrane potential between the T/4 passes when `v` is NULL */
+  float in_scalar;       /* SD_IN_TOKENS: the value of input channel 1 (diffusion time t as a float) */
 } sd_conv_args;
 
 int64_t sd_conv_weight_bytes_simt(const sd_conv_desc* d);

@@ -107,10 +107,10 @@ class ConvArgs(ctypes.Structure):
     _fields_ = [("in_", ctypes.c_void_p), ("in2", ctypes.c_void_p), ("weights", ctypes.c_void_p),
                 ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p), ("v", ctypes.c_void_p),
                 ("out", ctypes.c_void_p), ("out_sum", ctypes.c_void_p), ("memout_coef_host", ctypes.c_void_p),
-                ("workspace", ctypes.c_void_p)]
+                ("workspace", ctypes.c_void_p), ("in_scalar", ctypes.c_float)]
 
 
-IN_REAL_CONST, IN_REAL_SEQ, IN_STF, IN_STF8 = 0, 1, 2, 3
+IN_REAL_CONST, IN_REAL_SEQ, IN_STF, IN_STF8, IN_TOKENS = 0, 1, 2, 3, 4
 OUT_LIF, OUT_REAL_SEQ, OUT_MEMOUT_TANH, OUT_MEAN_T, OUT_LIF8 = 0, 1, 2, 3, 4
 SD_ERR_INVALID, SD_ERR_CUDA, SD_ERR_NO_DEVICE, SD_ERR_UNSUPPORTED = 1, 2, 3, 4
 

@@ -26,6 +26,7 @@ struct SimtParams {
   void* out;
   __half* out_sum;
   MemoutCoef coef;
+  float in_scalar;      // SD_IN_TOKENS: value of input channel 1
 };
 
 template <int TMAX>
@@ -293,6 +294,13 @@ template <int TMAX>
 __global__ void __launch_bounds__(256) conv_real_const_lif_kernel(const SimtParams p) {
   const sd_conv_desc& d = p.d;
   const int T = d.T, Cout = d.C_out, Cin = d.C_in;
+  // the whole weight block [kh*kw][C_in][C_out] (a few KB for the real-input layers: K-dim 9 / 18 / 16) is staged in
+  // shared memory once per block; threads of a warp share the output-channel chunk, so the reads are broadcasts
+  extern __shared__ float sw[];
+  for (int i = threadIdx.x; i < d.kh * d.kw * Cin * Cout; i += blockDim.x) sw[i] = p.w[i];
+  __syncthreads();
+  const bool tokens = d.in_kind == SD_IN_TOKENS;
+  const int64_t* __restrict__ tok = (const int64_t*)p.in;
   const int Cout8 = Cout >> 3;
   const int64_t npix = (int64_t)d.B * d.H_out * d.W_out;
   const int64_t total = npix * Cout8;
@@ -318,12 +326,14 @@ __global__ void __launch_bounds__(256) conv_real_const_lif_kernel(const SimtPara
       for (int kx = 0; kx < d.kw; ++kx) {
         const int ix = ox * d.stride - d.pad + kx;
         if (ix < 0 || ix >= d.W_in) continue;
-        const float* wt = p.w + (int64_t)(ky * d.kw + kx) * Cin * Cout + co;
+        const float* wt = sw + (ky * d.kw + kx) * Cin * Cout + co;
         const float* xp = xin + ((int64_t)b * Cin) * plane + (int64_t)iy * d.W_in + ix;
         for (int ci = 0; ci < Cin; ++ci) {
-          const float xv = xp[(int64_t)ci * plane];
-          const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt + (int64_t)ci * Cout));
-          const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + (int64_t)ci * Cout + 4));
+          // SD_IN_TOKENS: channel 0 = the token id as a float, channel 1 = the diffusion time (vq_diffusion.py:195-197)
+          const float xv = tokens ? (ci == 0 ? (float)tok[(int64_t)b * plane + (int64_t)iy * d.W_in + ix] : p.in_scalar)
+                                  : xp[(int64_t)ci * plane];
+          const float4 w0 = *reinterpret_cast<const float4*>(wt + ci * Cout);
+          const float4 w1 = *reinterpret_cast<const float4*>(wt + ci * Cout + 4);
           acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
           acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
           acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
@@ -694,7 +704,8 @@ int validate_conv_desc(const sd_conv_desc* d) {
   SD_REQUIRE(d->B >= 1 && d->C_in >= 1 && d->C_out >= 1 && d->H_in >= 1 && d->W_in >= 1 && d->H_out >= 1 &&
                  d->W_out >= 1, "conv: non-positive dimension");
   SD_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->stride >= 1 && d->pad >= 0, "conv: bad kernel/stride/padding");
-  SD_REQUIRE(d->in_kind >= SD_IN_REAL_CONST && d->in_kind <= SD_IN_STF8, "conv: bad in_kind %d", d->in_kind);
+  SD_REQUIRE(d->in_kind >= SD_IN_REAL_CONST && d->in_kind <= SD_IN_TOKENS, "conv: bad in_kind %d", d->in_kind);
+  if (d->in_kind == SD_IN_TOKENS) SD_REQUIRE(d->C_in == 2 && !d->transposed, "conv: SD_IN_TOKENS is the denoiser's 2-channel input");
   SD_REQUIRE(d->out_kind >= SD_OUT_LIF && d->out_kind <= SD_OUT_LIF8, "conv: bad out_kind %d", d->out_kind);
   if (d->in_kind == SD_IN_STF8) SD_REQUIRE(d->in_T == d->T && d->C_in0 == d->C_in && d->C_in % 16 == 0,
                                            "conv: STF8 input needs in_T == T, one segment, C_in %% 16 == 0");
@@ -754,6 +765,7 @@ int sd_conv_lif_simt(const sd_conv_desc* d, const sd_conv_args* a, void* stream)
   p.d = *d;
   p.in = a->in; p.in2 = a->in2; p.w = (const float*)a->weights; p.scale = a->scale; p.shift = a->shift;
   p.v = a->v; p.out = a->out; p.out_sum = (__half*)a->out_sum;
+  p.in_scalar = a->in_scalar;
   for (int t = 0; t < SD_MAX_T; ++t)
     p.coef.c[t] = (a->memout_coef_host && t < d->T) ? a->memout_coef_host[t] : 0.f;
   int64_t n = (int64_t)d->B * d->H_out * d->W_out * d->C_out;
@@ -761,20 +773,27 @@ int sd_conv_lif_simt(const sd_conv_desc* d, const sd_conv_args* a, void* stream)
   int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   cudaStream_t st = as_stream(stream);
-  if (d->in_kind == SD_IN_STF8 || (d->out_kind == SD_OUT_LIF8 && !(d->in_kind == SD_IN_REAL_CONST && !d->transposed))) {
+  if (d->in_kind == SD_IN_STF8 ||
+      (d->out_kind == SD_OUT_LIF8 && !((d->in_kind == SD_IN_REAL_CONST || d->in_kind == SD_IN_TOKENS) && !d->transposed))) {
     set_error("conv_simt: the u8 spike format (STF8) is produced by the constant-input layer and consumed by "
               "sd_conv_lif_tc (nsplit = 3) only");
     return SD_ERR_UNSUPPORTED;
   }
-  if (d->in_kind == SD_IN_REAL_CONST && (d->out_kind == SD_OUT_LIF || d->out_kind == SD_OUT_LIF8) && !d->transposed &&
-      d->C_out % 8 == 0) {
+  const size_t w_smem = (size_t)d->kh * d->kw * d->C_in * d->C_out * sizeof(float);
+  if (d->in_kind == SD_IN_TOKENS && !((d->out_kind == SD_OUT_LIF || d->out_kind == SD_OUT_LIF8) && d->C_out % 8 == 0 &&
+                                      w_smem <= 48 * 1024)) {
+    set_error("conv_simt: SD_IN_TOKENS needs a LIF output with C_out %% 8 == 0 and a weight block of at most 48 KB");
+    return SD_ERR_UNSUPPORTED;
+  }
+  if ((d->in_kind == SD_IN_REAL_CONST || d->in_kind == SD_IN_TOKENS) && (d->out_kind == SD_OUT_LIF || d->out_kind == SD_OUT_LIF8) &&
+      !d->transposed && d->C_out % 8 == 0 && w_smem <= 48 * 1024) {
     int64_t n8 = (int64_t)d->B * d->H_out * d->W_out * (d->C_out / 8);
     int64_t bl = (n8 + 255) / 256;
     if (bl > cap) bl = cap;
-    if (d->T <= 4) conv_real_const_lif_kernel<4><<<(unsigned)bl, 256, 0, st>>>(p);
-    else if (d->T <= 8) conv_real_const_lif_kernel<8><<<(unsigned)bl, 256, 0, st>>>(p);
-    else if (d->T <= 16) conv_real_const_lif_kernel<16><<<(unsigned)bl, 256, 0, st>>>(p);
-    else conv_real_const_lif_kernel<32><<<(unsigned)bl, 256, 0, st>>>(p);
+    if (d->T <= 4) conv_real_const_lif_kernel<4><<<(unsigned)bl, 256, w_smem, st>>>(p);
+    else if (d->T <= 8) conv_real_const_lif_kernel<8><<<(unsigned)bl, 256, w_smem, st>>>(p);
+    else if (d->T <= 16) conv_real_const_lif_kernel<16><<<(unsigned)bl, 256, w_smem, st>>>(p);
+    else conv_real_const_lif_kernel<32><<<(unsigned)bl, 256, w_smem, st>>>(p);
     SD_LAUNCH_CHECK();
     return SD_OK;
   }

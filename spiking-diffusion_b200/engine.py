@@ -261,8 +261,9 @@ class FusedLayer:
         return torch.full((n,), d.v_reset if d.hard_reset else 0.0, dtype=torch.float32, device=self.device)
 
     def run(self, x: torch.Tensor, out: torch.Tensor, x2: Optional[torch.Tensor] = None,
-            out_sum: Optional[torch.Tensor] = None, v: Optional[torch.Tensor] = None) -> torch.Tensor:
+            out_sum: Optional[torch.Tensor] = None, v: Optional[torch.Tensor] = None, in_scalar: float = 0.0) -> torch.Tensor:
         a = ConvArgs()
+        a.in_scalar = float(in_scalar)
         a.in_, a.in2, a.weights = ptr(x), ptr(x2), ptr(self.wpack)
         a.scale, a.shift, a.v = ptr(self.scale), ptr(self.shift), ptr(v)
         a.out, a.out_sum = ptr(out), ptr(out_sum)
@@ -294,6 +295,10 @@ class DenoiserPlan:
         ns = 3 if self.i8 else (2 if nsplit == 3 else nsplit)
         self.l1 = mk(model.conv1, wf and wf.l1, in_kind=_lib.IN_REAL_CONST,
                      out_kind=_lib.OUT_LIF8 if self.i8 else _lib.OUT_LIF, impl="simt")
+        # the sampler's entry: conv1 reads the int64 token grid and the scalar diffusion time directly
+        # (cat(x, t * ones) -> repeat(T) of vq_diffusion.py:195-198 is never materialised); same packed weights
+        self.l1t = mk(model.conv1, self.l1, in_kind=_lib.IN_TOKENS,
+                      out_kind=_lib.OUT_LIF8 if self.i8 else _lib.OUT_LIF, impl="simt")
         mk_s = lambda seq, sh: FusedLayer(seq[0], seq[1], seq[2], T=T, B=b, H_in=h, W_in=w, nsplit=ns, share=sh,
                                           concurrent=concurrent, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF, impl=impl)
         self.l2 = mk_s(model.conv2, wf and wf.l2)
@@ -320,8 +325,11 @@ class DenoiserPlan:
             return stf8_to_nchw(buf, lyr.T, lyr.B, lyr.C_out, lyr.H_out, lyr.W_out)
         return stf_to_nchw(buf, lyr.T, lyr.B, lyr.C_out, lyr.H_out, lyr.W_out)
 
-    def run_from_input(self) -> torch.Tensor:
-        self.l1.run(self.xin, self.x1, out_sum=self.x1s)
+    def run_from_input(self, tokens: Optional[torch.Tensor] = None, t: float = 0.0) -> torch.Tensor:
+        if tokens is None:
+            self.l1.run(self.xin, self.x1, out_sum=self.x1s)
+        else:
+            self.l1t.run(tokens, self.x1, out_sum=self.x1s, in_scalar=t)
         self.l2.run(self.x1, self.x2)
         self.l3.run(self.x2, self.x3)
         self.l4.run(self.x3, self.x4)
@@ -331,8 +339,7 @@ class DenoiserPlan:
 
     def run_tokens(self, x_t: torch.Tensor, t: int) -> torch.Tensor:
         """x_t int64 [b*h*w] token ids, scalar diffusion time t (the sampler uses one t for the whole batch)."""
-        check(lib().sd_denoiser_input(ptr(x_t), ptr(self.xin), self.b, self.h, self.w, int(t), stream_ptr()))
-        return self.run_from_input()
+        return self.run_from_input(x_t, float(int(t)))
 
     def run(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
         """General entry: x float [b,1,h,w], t long [b] (per-sample times, as DummyModel.forward allows)."""
@@ -425,7 +432,7 @@ class SamplerPlan:
         self.inc_u = inc.value
         check(lib().sd_philox_offset_increment(self.n_tokens_global * self.K, ctypes.byref(inc)))
         self.inc_e = inc.value
-        self.kernel_launches_per_step = 8 * len(self.subs)
+        self.kernel_launches_per_step = 7 * len(self.subs)     # conv1 (token input) .. conv6, sampling step
 
     def flops_per_image(self, sample_steps: int) -> int:
         return sum(dp.flops() for dp, _, _ in self.subs) * sample_steps // self.b

@@ -316,3 +316,18 @@ def test_model_on_a_non_current_device_runs_there():
     b = den0(x.cuda(), t.cuda())
     assert a.device.index == 1 and torch.equal(a.cpu(), b.cpu())
     functional.reset_net(den); functional.reset_net(den0)
+
+
+def test_denoiser_token_input_equals_materialised_input():
+    """The sampler's conv1 reads the int64 token grid and the scalar time directly (SD_IN_TOKENS); the general entry
+    materialises cat(x, t * ones) first (vq_diffusion.py:195-197).  Same kernel arithmetic -> bit-identical logits."""
+    den, _ = make_denoiser(4, 128, seed=1)
+    b = 6
+    g = torch.Generator().manual_seed(3)
+    tok = torch.randint(0, 129, (b, 1, 7, 7), generator=g).cuda()
+    plan = den.plan(b, 7, 7)
+    a = plan.run_tokens(tok.reshape(-1), 13).clone()
+    bb = plan.run(tok.float(), torch.full((b,), 13, dtype=torch.long, device="cuda")).clone()
+    assert torch.equal(a, bb)
+    x1 = plan.spikes_nchw(plan.x1, plan.l1)
+    assert 0.01 < float(x1.mean()) < 0.6
