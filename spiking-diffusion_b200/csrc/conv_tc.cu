@@ -60,6 +60,10 @@ constexpr int kRegsOther = 128;        // warps 8-11 after setmaxnreg.dec
 constexpr int kRegsEpilogue = 192;    // warps 0-7 after setmaxnreg.inc: 256 * 216 + 128 * 72 = 64512 <= 65536
 constexpr int kMaxAStages = 4;
 constexpr int kMaxBStages = 8;
+#ifndef SD_TC_B_PIECES
+#define SD_TC_B_PIECES 1
+#endif
+constexpr int kBPieces = SD_TC_B_PIECES;   // concurrent bulk copies per weight stage
 constexpr uint32_t kSmemBudget = 220 * 1024;
 // shared-memory header: barriers + TMEM slot in the first 1 KB, then two buffers of (scale[256], shift[256]) for the
 // epilogue (the N tile's folded-BN affine, staged while the MMAs of the tile run)
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
       }
     }
   } else if (warp == kWarpB) {
-    // ===== B producer (whole warp converged; one elected lane issues) =====
+    // ===== B producer (whole warp converged; kBPieces lanes issue one bulk copy each per stage) =====
     PipeState st;
     const int64_t stage_halfs = c.b_stage_bytes / 2;
     const int halves = PAIR ? 2 : 1;                 // pair: each CTA stages its own half (N/2 rows) of every B block
@@ -439,10 +443,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
         const int it = itt % (c.num_kblocks * 9);      // every T pass streams the same weights again
         const int kb = it / 9, tap = tap_order(it - kb * 9);
         mbar_wait(b_empty(st.stage), st.phase ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(b_full(st.stage), c.b_stage_bytes);
-          bulk_g2s(b_base + st.stage * c.b_stage_bytes, wsrc + (int64_t)(kb * 9 + tap) * stage_halfs * halves,
-                   c.b_stage_bytes, b_full(st.stage));
+        if (lane == 0) mbar_expect_tx(b_full(st.stage), c.b_stage_bytes);
+        __syncwarp();
+        // One bulk copy per stage (kBPieces = 1).  Measured: the weight stream arrives at ~16 B/clk per SM, which is what
+        // the MMAs of a stage consume at 2 timesteps per pass; cutting a stage into 8 concurrent copies was slower
+        // (conv5 MMA phase 58.6 k -> 62 k cycles), and one timestep per pass (twice the weight traffic) is weight-bound.
+        if (lane < kBPieces) {
+          const uint32_t piece = c.b_stage_bytes / kBPieces;        // stage sizes are multiples of 1 KB
+          bulk_g2s(b_base + st.stage * c.b_stage_bytes + lane * piece,
+                   reinterpret_cast<const uint8_t*>(wsrc + (int64_t)(kb * 9 + tap) * stage_halfs * halves) + lane * piece,
+                   piece, b_full(st.stage));
         }
         __syncwarp();
         st.advance(c.b_stages);
@@ -1036,8 +1046,10 @@ static int tc_supported(const sd_conv_desc* d, const char** why) {
 static int tc_config_i8(const sd_conv_desc* d, TcConfig* c) {
   check_device();
   const int sms = sm_count() > 0 ? sm_count() : 148;
-  c->T_acc = 2;
-  c->n_tchunks = d->T / 2;
+  // 2 timesteps per pass fill TMEM with hi + lo accumulators (one stage); SD_TC_TACC=1: one timestep per pass and two
+  // accumulator stages (the epilogue of a pass overlaps the MMAs of the next) at twice the weight traffic
+  c->T_acc = knobs().tacc == 1 ? 1 : 2;
+  c->n_tchunks = d->T / c->T_acc;
   c->ndx = 1;
   const int64_t rows = (int64_t)d->B * d->H_in * d->W_in;
   const int m_tiles = (int)((rows + kTileRows - 1) / kTileRows);
