@@ -13,6 +13,7 @@ PROF = os.path.join(ROOT, "profiles")
 KEYS = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor_subpipe_imma.avg.pct_of_peak_sustained_active",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
@@ -73,9 +74,9 @@ def summarize_launches(csvf, out, title):
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             f.write(f"{k:44s} {len(v):8d} {sum(v):11.1f} {sum(v) / len(v):9.2f} {100 * sum(v) / tot:6.1f}%\n")
         f.write(f"{'TOTAL':44s} {sum(len(v) for v in agg.values()):8d} {tot:11.1f}\n\n# one diffusion step, in launch order:\n")
-        start = next((i for i, s in enumerate(seq) if s[0].startswith("denoiser_input")), 0)
+        start = next((i for i, s in enumerate(seq) if s[0].startswith("conv_real_const_lif")), 0)
         f.write("# (sub-batch 0 of 5; the other sub-batches follow in the same order)\n")
-        for name, grid, v in seq[start:start + 8]:
+        for name, grid, v in seq[start:start + 7]:
             f.write(f"  {name:44s} grid {grid:14s} {v:9.2f} us\n")
         first_dec = next((i for i, s in enumerate(seq) if s[0].startswith("vq_gather")), None)
         f.write("\n# decode after the last diffusion step, in launch order:\n")
@@ -84,7 +85,7 @@ def summarize_launches(csvf, out, title):
     print("wrote", out)
 
 
-def write_traffic(rep, n_subs=5, workload="cfg2"):
+def write_traffic(rep, n_subs=5, workload="cfg2", tag="r01"):
     """profiles/traffic.json: DRAM bytes per LAUNCH GROUP (the layer's launches of all sub-batches of one diffusion
     step).  The capture holds 5 tcgen05 layers x n_subs sub-batches in launch order (sub-batch major)."""
     import json
@@ -99,7 +100,7 @@ def write_traffic(rep, n_subs=5, workload="cfg2"):
         return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(units[i].lower(), 1)
 
     out = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per LAUNCH GROUP (the layer's launches of all "
-                       f"{n_subs} sub-batches of one diffusion step), summed from profiles/r01_conv3x3_tc.txt "
+                       f"{n_subs} sub-batches of one diffusion step), summed from profiles/{tag}_conv3x3_tc.txt "
                        "(ncu --set full, cold cache, serialised)"}
     for li, name in enumerate(("conv2", "conv3", "conv4", "conv5", "conv6")):
         tot = sum(val(rows[s * 5 + li], "dram__bytes_read.sum") + val(rows[s * 5 + li], "dram__bytes_write.sum")
@@ -120,5 +121,5 @@ if __name__ == "__main__":
                              ("p_conv1.ncu-rep", "conv_real_const_lif", "den.conv1: real-input conv + BN + LIF (cfg2)")):
         if os.path.exists(os.path.join(OUT, rep)):
             if name == "conv3x3_tc":
-                write_traffic(os.path.join(OUT, rep))
+                write_traffic(os.path.join(OUT, rep), tag=tag)
             summarize_rep(os.path.join(OUT, rep), os.path.join(PROF, f"{tag}_{name}.txt"), title)

@@ -60,7 +60,7 @@ def main():
         note = "" if n_flips == 0 else (f"; {n_flips} near-threshold neuron-timestep(s) flipped, so {int((err > 1e-3).sum())} "
                                         f"of {err.numel()} pixels in their receptive fields differ (mean-abs error {float(err.mean()):.2e})")
         print(f"reconstruction max-abs error {float(err.max()):.3e} (tolerance 1e-3 when no spike moved){note}")
-    for T, b, K, hw, nsplit in ((4, 16, 128, 7, 2), (4, 16, 128, 7, 1), (8, 8, 512, 7, 2), (4, 8, 128, 8, 2), (16, 4, 128, 7, 2)):
+    for T, b, K, hw, nsplit in ((4, 16, 128, 7, 3), (4, 16, 128, 7, 2), (4, 16, 128, 7, 1), (8, 8, 512, 7, 3), (4, 8, 128, 8, 3), (16, 4, 128, 7, 3)):
         m, sd = make_denoiser(T, K, seed=2)
         m.nsplit = nsplit
         g = torch.Generator().manual_seed(5)
