@@ -33,10 +33,23 @@ def test_library_exports_every_declared_symbol():
     assert exported == set(header_symbols())
 
 
-def test_struct_layout_matches_header():
-    # 17 ints + 3 floats + 3 ints, no padding; 10 pointers
+def test_struct_layout_matches_header(tmp_path):
+    """The ctypes mirrors of sd_conv_desc / sd_conv_args against what a C compiler makes of include/sd_b200.h."""
+    import subprocess
+    # 17 ints + 3 floats + 3 ints, no padding; 10 pointers + one float (padded to pointer alignment)
     assert ctypes.sizeof(_lib.ConvDesc) == 23 * 4
-    assert ctypes.sizeof(_lib.ConvArgs) == 10 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_lib.ConvArgs) == 11 * ctypes.sizeof(ctypes.c_void_p)
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sd_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(sd_conv_desc), sizeof(sd_conv_args), '
+                   'offsetof(sd_conv_desc, tau), offsetof(sd_conv_desc, concurrent), offsetof(sd_conv_args, workspace), '
+                   'offsetof(sd_conv_args, in_scalar)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(_lib.ConvDesc), ctypes.sizeof(_lib.ConvArgs), _lib.ConvDesc.tau.offset, _lib.ConvDesc.concurrent.offset,
+            _lib.ConvArgs.workspace.offset, _lib.ConvArgs.in_scalar.offset]
+    assert got == want, (got, want)
 
 
 def test_geometry_queries_are_host_only():
