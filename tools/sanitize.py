@@ -46,5 +46,21 @@ functional.reset_net(vae)
 lg_t = den(torch.randint(0, K + 1, (4, 1, 7, 7)).float().cuda(), torch.randint(1, 50, (4,)).cuda())
 lg_t.square().mean().backward()
 functional.reset_net(den)
+# round 2: the kind::f16 denoiser path (the default is kind::i8, exercised above), a T-parallel int8 layer (lone small
+# batch at T = 8 -> above), chunked sampling from one plan, and the metric kernels
+den.eval(); vae.eval()
+den.nsplit = 2
+ab2 = AbsorbingDiffusion(den, mask_id=K, shape=(7, 7), n_samples=5)
+ab2.max_plan_batch = 2
+tok5 = ab2.sample(temp=1.0, sample_steps=2, seed=3)
+den.nsplit = 3
+from spiking_diffusion_b200 import metric  # noqa: E402
+a_img, b_img = torch.rand(3, 1, 28, 28, device="cuda") - 0.5, torch.rand(3, 1, 28, 28, device="cuda") - 0.5
+ssim_v, mse_v = metric.pytorch_ssim.SSIM(window_size=11)(a_img, b_img), metric.mse_loss(a_img, b_img)
+f1, f2 = torch.randn(40, 33, device="cuda", dtype=torch.float64), torch.randn(50, 33, device="cuda", dtype=torch.float64) + 0.1
+fid = metric.Fid_score.calculate_fid_from_features(f1, f2)
+mmd = metric.kid.poly_mmd(f1[:37].float(), f2[:37].float())
+is_m, is_s = metric.IS_score.inception_score_from_probs(torch.softmax(torch.randn(30, 17, device="cuda", dtype=torch.float64), 1), 3)
 torch.cuda.synchronize()
+print("metrics", float(ssim_v), float(mse_v), float(fid), float(mmd), float(is_m))
 print("sanitize pass done", float(rec.abs().max()), int(tok.max()), float(pred.abs().max()), float(lg.abs().max()))
