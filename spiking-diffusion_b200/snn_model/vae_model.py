@@ -74,24 +74,21 @@ class VectorQuantizer(nn.Module):
         return quantized, encoding_indices
 
     def _forward_train(self, x: torch.Tensor):
-        """Training branch, operation for operation as vae_model.py:42-85 with num_step := T."""
-        T = x.shape[0]
-        x_memout = (1 - self.alpha) * self.memout(x) + self.alpha * torch.sum(x, dim=0) / T
-        x_memout = x_memout.permute(0, 2, 3, 1).contiguous()
-        flat_x = x_memout.reshape(-1, self.embedding_dim)
-        encoding_indices = self.get_code_indices(flat_x.detach())          # argmin: no gradient
-        quantized = F.embedding(encoding_indices, self.embeddings.weight).view_as(x_memout)
-        q_latent_loss = F.mse_loss(quantized, x_memout.detach())
-        e_latent_loss = F.mse_loss(x_memout, quantized.detach())
-        loss_1 = q_latent_loss + self.commitment_cost * e_latent_loss
-        quantized = x_memout + (quantized - x_memout).detach()             # straight-through estimator
-        quantized = quantized.permute(0, 3, 1, 2).contiguous()
-        quantized = torch.unsqueeze(quantized, dim=0).repeat(T, 1, 1, 1, 1)
-        quantized = self.poisson(quantized)
-        q_latent_loss_2 = torch.mean((self.psp(quantized) - self.psp(x.detach())) ** 2)
-        e_latent_loss_2 = torch.mean((self.psp(quantized.detach()) - self.psp(x)) ** 2)
-        loss_2 = q_latent_loss_2 + self.commitment_cost * e_latent_loss_2
-        return quantized, loss_1 + loss_2
+        """Training branch (vae_model.py:42-85 with num_step := T): quantise the firing-rate / membrane feature with a
+        straight-through estimator, regenerate spikes from the codes, and penalise both the feature distance (loss_1) and the
+        distance between the post-synaptic potentials of the regenerated and the original spike trains (loss_2), each as
+        codebook term + commitment_cost * commitment term."""
+        T, beta = x.shape[0], self.commitment_cost
+        feature = ((1 - self.alpha) * self.memout(x) + self.alpha * torch.sum(x, dim=0) / T).permute(0, 2, 3, 1).contiguous()
+        idx = self.get_code_indices(feature.detach().reshape(-1, self.embedding_dim))          # argmin: no gradient
+        codes = F.embedding(idx, self.embeddings.weight).view_as(feature)
+        loss_1 = F.mse_loss(codes, feature.detach()) + beta * F.mse_loss(feature, codes.detach())
+        straight_through = feature + (codes - feature).detach()
+        regenerated = self.poisson(straight_through.permute(0, 3, 1, 2).contiguous().unsqueeze(0).repeat(T, 1, 1, 1, 1))
+        psp = self.psp
+        loss_2 = (torch.mean((psp(regenerated) - psp(x.detach())) ** 2)
+                  + beta * torch.mean((psp(regenerated.detach()) - psp(x)) ** 2))
+        return regenerated, loss_1 + loss_2
 
     @on_device_of
     def forward_with_loss(self, x: torch.Tensor):

@@ -27,19 +27,16 @@ def get_data_for_diff(train_loader, model, T: int = None):
     Like the reference, the model is put in eval mode and is NOT reset between batches, so LIF membrane state leaks
     from one batch into the next; call ``functional.reset_net(model)`` per batch
     yourself if that is not wanted.  ``T`` defaults to the model's timestep count (the reference hard-codes 16)."""
-    print('prepare data for train diffusion...')
+    print('prepare data for train diffusion...')          # the reference's progress line (vq_diffusion.py:24)
     model.eval()
-    T = getattr(model, "T", 16) if T is None else T
-    train_indices = []
-    for images, labels in train_loader:
-        images = images - 0.5  # normalize to [-0.5, 0.5]
-        images = images.cuda()
-        images_spike = images.unsqueeze(0).repeat(T, 1, 1, 1, 1)
-        with torch.inference_mode():
-            _, _, encoding_indices = model(images_spike, images)
-            h, w = images.shape[-2] // 4, images.shape[-1] // 4
-            train_indices.append(encoding_indices.reshape(images.shape[0], h, w).cpu())
-    return train_indices
+    steps = getattr(model, "T", 16) if T is None else T
+    grids = []
+    with torch.inference_mode():
+        for batch, _labels in train_loader:
+            frame = (batch - 0.5).cuda()                                    # ToTensor() range -> [-0.5, 0.5]
+            codes = model(frame.unsqueeze(0).repeat(steps, 1, 1, 1, 1), frame)[2]   # direct encoding: the frame at every timestep
+            grids.append(codes.reshape(frame.shape[0], frame.shape[-2] // 4, frame.shape[-1] // 4).cpu())
+    return grids
 
 
 def load_reference_state_dict(module, state_dict, strict: bool = True):
@@ -143,38 +140,34 @@ class AbsorbingDiffusion(engine.PlanCacheMixin, Sampler):
         return t, pt
 
     def q_sample(self, x_0, t):
-        """Forward (masking) process (vq_diffusion.py:61-72); plain tensor algebra, training path only."""
-        x_t, x_0_ignore = x_0.clone(), x_0.clone()
-        t_mask = t.reshape(x_0.shape[0], 1, 1, 1).expand(x_0.shape[0], 1, *self.shape)
-        mask = torch.rand_like(x_t.float()) < (t_mask.float() / self.num_timesteps)
-        x_t[mask] = self.mask_id
-        x_0_ignore[torch.bitwise_not(mask)] = -1
-        return x_t, x_0_ignore, mask
+        """Forward (masking) process of the absorbing diffusion (vq_diffusion.py:61-72): token (b, i) is replaced by the mask
+        id with probability t_b / num_timesteps.  Returns (x_t, targets with -1 where nothing was masked, mask).  One uniform
+        per token from torch's generator, drawn like the reference's ``rand_like`` (same shape, dtype, device)."""
+        p_mask = t.to(torch.float32).view(-1, 1, 1, 1) / self.num_timesteps
+        mask = torch.rand_like(x_0, dtype=torch.float32) < p_mask
+        return x_0.masked_fill(mask, self.mask_id), x_0.masked_fill(~mask, -1), mask
 
     def _train_loss(self, x_0):
-        """Re-weighted ELBO of the absorbing diffusion (vq_diffusion.py:75-101); x_0: [b, 1, h, w] token ids."""
-        b, device = x_0.size(0), x_0.device
+        """ELBO / re-weighted ELBO of the absorbing diffusion (vq_diffusion.py:75-101); x_0: [b, 1, h, w] token ids.  The
+        cross entropy over the masked tokens (the others carry the ignore index) is summed per sample; 'elbo' divides it by
+        t and by the probability 1/num_timesteps of having drawn that t, 'reweighted_elbo' weights it by 1 - t/num_timesteps;
+        both are expressed in bits per token."""
+        b = x_0.size(0)
         n_tok = self.shape[0] * self.shape[1]
-        t, pt = self.sample_time(b, device)
-        x_t, x_0_ignore, mask = self.q_sample(x_0=x_0, t=t)
-        x_0_hat_logits = self._denoise_fn(x_t, t=t)
-        cross_entropy_loss = F.cross_entropy(x_0_hat_logits.reshape(b, self.num_classes, n_tok),
-                                             x_0_ignore.reshape(b, n_tok).long(), ignore_index=-1,
-                                             reduction='none').sum(1)
-        vb_loss = cross_entropy_loss / t
-        vb_loss = vb_loss / pt
-        vb_loss = vb_loss / (math.log(2) * x_0.shape[1:].numel())
+        t, pt = self.sample_time(b, x_0.device)
+        x_t, target, _ = self.q_sample(x_0=x_0, t=t)
+        logits = self._denoise_fn(x_t, t=t)                                              # [b, K, h, w]
+        nll = F.cross_entropy(logits.reshape(b, self.num_classes, n_tok), target.reshape(b, n_tok).long(),
+                              ignore_index=-1, reduction='none').sum(1)
+        bits = math.log(2) * x_0.shape[1:].numel()
         if self.loss_type == 'elbo':
-            loss = vb_loss
+            per_sample = nll / t / pt / bits
         elif self.loss_type == 'reweighted_elbo':
-            weight = (1 - (t / self.num_timesteps))
-            loss = weight * cross_entropy_loss
-            loss = loss / (math.log(2) * x_0.shape[1:].numel())
+            per_sample = (1 - (t / self.num_timesteps)) * nll / bits
         else:
             raise ValueError
-        return loss.mean()
+        return per_sample.mean()
 
-    @on_device_of
     def train_iter(self, x):
         return {"loss": self._train_loss(x)}
 
