@@ -288,7 +288,7 @@ def test_stride2_conv_as_subsampled_tc_conv_matches_oracle_and_simt(cin, cout, B
     assert float((g_tc != g_simt).float().mean()) <= 1e-4
 
 
-@pytest.mark.parametrize("impl", ["tc", "simt"])
+@pytest.mark.parametrize("impl", ["tc", "tc-i8", "simt"])
 @pytest.mark.parametrize("tau,v_th,v_reset", [(2.0, 1.0, None), (3.0, 0.7, 0.0), (2.0, 1.0, -0.25), (4.0, 0.5, None)])
 def test_fused_layer_with_general_lif_parameters(impl, tau, v_th, v_reset):
     """Soft reset, tau that is not a power of two, non-zero reset value and threshold: the general LIF branch of the
@@ -296,14 +296,16 @@ def test_fused_layer_with_general_lif_parameters(impl, tau, v_th, v_reset):
     T, B, H, cin, cout = 4, 6, 7, 64, 128
     seq, p = make_block(cin, cout, seed=21)
     lif = neuron.LIFNode(tau=tau, v_threshold=v_th, v_reset=v_reset, surrogate_function=surrogate.ATan(), step_mode="m")
+    i8 = impl == "tc-i8"     # the int8-digit kernel (two passes at T = 4: the potential crosses a pass boundary in shared memory)
     layer_ = engine.FusedLayer(seq[0], seq[1], lif, T=T, B=B, H_in=H, W_in=H, in_kind=_lib.IN_STF, out_kind=_lib.OUT_LIF,
-                               impl=impl)
+                               impl="tc" if i8 else impl, nsplit=3 if i8 else 2)
     s_in = spikes((T, B, cin, H, H), 0.12, 3)
     cur = O.conv_bn(s_in, p, "c", "b", padding=1)
     s_ref, v_ref, h_ref = O.lif_multi_step(cur, tau=tau, v_threshold=v_th, v_reset=v_reset, return_h=True)
     v = layer_.alloc_state()
-    out = layer_.run(engine.stf_from_nchw(s_in.cuda()), layer_.alloc_out(), v=v)
-    got = engine.stf_to_nchw(out, T, B, cout, H, H)
+    x_in = engine.stf8_from_nchw(s_in.cuda()) if i8 else engine.stf_from_nchw(s_in.cuda())
+    out = layer_.run(x_in, layer_.alloc_out(), v=v)
+    got = engine.stf8_to_nchw(out, T, B, cout, H, H) if i8 else engine.stf_to_nchw(out, T, B, cout, H, H)
     assert_spikes_match(got, s_ref, h_ref, f"{impl} tau={tau} v_th={v_th} v_reset={v_reset}", v_th=v_th)
     v_got = torch.empty((B, cout, H, H), dtype=torch.float32, device="cuda")
     _lib.check(_lib.lib().sd_state_convert(_lib.ptr(v), _lib.ptr(v_got), B, cout, H, H, 0, _lib.stream_ptr()))
