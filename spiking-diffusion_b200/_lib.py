@@ -275,6 +275,9 @@ def on_device_of(fn):
     @functools.wraps(fn)
     def wrapper(*args, **kwargs):
         import torch
+        seen = getattr(_tls, "devices", None)
+        if seen:
+            seen.clear()        # nothing may be left over from a call that raised between ptr() and stream_ptr()
         dev = first_cuda_device(*args, *kwargs.values())
         if dev is None or dev.index == torch.cuda.current_device():
             return fn(*args, **kwargs)

@@ -291,7 +291,7 @@ class DenoiserPlan:
         # nsplit = 3: conv2..conv5 on the kind::i8 tensor-core path (u8 spikes between the layers, three int8 weight
         # digits, exact int32 accumulation: 3 MMAs per 32 input channels where two fp16 terms need 4).  It needs an even
         # T; the read-out layer consumes T-summed counts (up to T per element) and stays on the fp16 path.
-        self.i8 = nsplit == 3 and T % 2 == 0 and impl != "simt"
+        self.i8 = nsplit == 3 and T % 2 == 0 and impl != "simt" and self._int8_layers_supported(model, T, b, h, w)
         ns = 3 if self.i8 else (2 if nsplit == 3 else nsplit)
         self.l1 = mk(model.conv1, wf and wf.l1, in_kind=_lib.IN_REAL_CONST,
                      out_kind=_lib.OUT_LIF8 if self.i8 else _lib.OUT_LIF, impl="simt")
@@ -314,6 +314,22 @@ class DenoiserPlan:
         self.x2, self.x3, self.x4 = self.l2.alloc_out(), self.l3.alloc_out(), self.l4.alloc_out()
         self.x5, self.x5s = self.l5.alloc_out(), self.l5.alloc_sum()
         self.logits = self.l6.alloc_out()  # [b, h, w, K] channels last
+
+    @staticmethod
+    def _int8_layers_supported(model, T, b, h, w) -> bool:
+        """Whether sd_conv_lif_tc takes conv2..conv5 of this shape as kind::i8 layers (channel multiples, grid width); if not,
+        the plan uses two fp16 terms (or the CUDA-core kernels) exactly as with nsplit = 2."""
+        for seq in (model.conv2, model.conv3, model.conv4, model.conv5):
+            conv = seq[0]
+            d = ConvDesc()
+            d.T, d.B, d.C_in, d.H_in, d.W_in = T, b, conv.in_channels, h, w
+            d.C_out, d.H_out, d.W_out = conv.out_channels, h, w
+            d.kh, d.kw, d.stride, d.pad, d.transposed = conv.kernel_size[0], conv.kernel_size[1], conv.stride[0], conv.padding[0], 0
+            d.in_kind, d.out_kind, d.in_T, d.C_in0 = _lib.IN_STF8, _lib.OUT_LIF8, T, conv.in_channels
+            d.tau, d.v_threshold, d.v_reset, d.hard_reset, d.nsplit, d.concurrent = 2.0, 1.0, 0.0, 1, 3, 1
+            if not lib().sd_conv_tc_supported(ctypes.byref(d)):
+                return False
+        return True
 
     def flops(self) -> int:
         return sum(l.flops() for l in self.layers)
