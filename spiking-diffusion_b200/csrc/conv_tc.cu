@@ -56,8 +56,8 @@ constexpr int kEpiWarps = SD_TC_EPI_WARPS;          // epilogue warps: 8 or 12 (
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kTcThreads = kEpiThreads + 128;       // + A producer, B producer, MMA issuer, TMEM allocator / relay
 constexpr int kWarpA = kEpiWarps, kWarpB = kEpiWarps + 1, kWarpMma = kEpiWarps + 2, kWarpAux = kEpiWarps + 3;
-constexpr int kRegsOther = 128;        // warps 8-11 after setmaxnreg.dec
-constexpr int kRegsEpilogue = 192;    // warps 0-7 after setmaxnreg.inc: 256 * 216 + 128 * 72 = 64512 <= 65536
+[[maybe_unused]] constexpr int kRegsOther = 128;        // warps 8-11 after setmaxnreg.dec (SD_TC_SETMAXNREG experiment)
+[[maybe_unused]] constexpr int kRegsEpilogue = 192;    // warps 0-7 after setmaxnreg.inc: 256 * 216 + 128 * 72 = 64512 <= 65536
 constexpr int kMaxAStages = 4;
 constexpr int kMaxBStages = 8;
 #ifndef SD_TC_B_PIECES
@@ -122,7 +122,8 @@ struct TcParams {
   int dbg;                  // diagnostics (env SD_TC_DBG): 1 = skip the spike stores, 2 = skip the TMEM loads
   TcConfig c;
 };
-[[maybe_unused]] constexpr int kTraceStride = 64;   // int64 slots per CTA: [0] entry, [1] set-up done, [2] exit, then 8 per tile pass
+[[maybe_unused]] constexpr int kTraceStride = 128;  // int64 slots per CTA: [0] entry, [1] set-up done, [2] exit, then 8 per tile pass;
+                                                     // from 64: warp 0's column groups of pass 1 (4 stamps each: start, state loaded, LIF done, end)
 
 // ---------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -635,6 +636,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
           sH[e] = in ? __ldg(p.shift + n0 + e) : 0.f;
         }
       }
+      // lean i8 LIF epilogue (below): everything that is fixed for the pass, computed while the MMAs of the pass still run
+      const uint32_t t_base0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc.stage * c.T_acc * ACCS * c.N_TILE);
+      const bool lean = I8 && p.out_kind == SD_OUT_LIF && !c.tpar && fast_lif && n0 + col_lo < p.Cout;
+      const bool v_via_smem = s_v != nullptr;
+      const bool want_sum = p.out_sum != nullptr, want_spk = p.out_spk8 != nullptr;
+      const int T_acc = c.T_acc;
+      const uint32_t n_tile = (uint32_t)c.N_TILE;
+      const float vth = p.v_th;
+      const int64_t row_off = p.G + r;
+      int64_t grp_bytes = p.R_alloc * 16;                       // next 16-channel chunk of an STF8 plane
+      int64_t plane = (int64_t)(p.Cout8 >> 1) * grp_bytes;      // from the s plane to the 128*s plane of a timestep
+      asm volatile("" : "+l"(grp_bytes), "+l"(plane));          // keep them in registers (no re-derivation per store)
+      const int64_t chunk0 = (int64_t)((n0 + col_lo) >> 3) * p.R_alloc + row_off;   // 8-channel chunk index of group 0
+      uint8_t* o_grp = p.out_spk8 + (int64_t)(tch * T_acc * 2) * plane + (chunk0 - ((int64_t)((n0 + col_lo) >> 4)) * p.R_alloc) * 16;
+      float* v_grp = p.v != nullptr ? p.v + chunk0 * 8 : nullptr;            // state plane [C/8][R_alloc][8] fp32
+      __half* sum_grp = want_sum ? p.out_sum + chunk0 * 8 : nullptr;         // T-sums [C/8][R_alloc][8] fp16
+      const int64_t chunk_stride = p.R_alloc * 8;                            // elements to the next 8-channel chunk
+      float* sv = s_v + threadIdx.x;                                         // [column][thread]
+      const float* aS = sS + col_lo;
+      const float* aH = sH + col_lo;
+      uint32_t t_grp = t_base0 + (uint32_t)col_lo;
+      const int last_col = min(col_hi, p.Cout - n0);                         // groups with n < Cout
+      const bool load_v_global = p.v != nullptr && valid && (!first_pass || p.v_load_initial) && !(v_via_smem && !first_pass);
+      const bool load_sum = !first_pass && want_sum && valid;
+      const bool store_v_global = p.v != nullptr && valid && (v_via_smem ? (last_pass && p.v_store_final) : (!last_pass || p.v_store_final));
+      asm volatile("" : "+l"(o_grp), "+l"(v_grp), "+l"(sum_grp), "+r"(t_grp));   // ... and kept above the wait
       asm volatile("" ::"r"(n0), "r"(pp), "r"(py), "r"(px));   // keep the tile's index arithmetic (divisions) above the wait
       mbar_wait(acc_full(sc.stage), sc.phase);
       tc_fence_after();
@@ -656,9 +683,117 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
           for (int j = 0; j < 16; ++j) a[j] = __float_as_uint(__int2float_rn((int)a[j] * 256 + (int)lo[j]));
         }
       };
-      for (int cc = col_lo; cc < col_hi; cc += 16) {
+      // ---- kind::i8, LIF with hard reset to 0 and tau a power of two (every layer of the denoiser): lean path ----
+      // Same arithmetic as the general code below, but everything that does not change inside a pass is computed once
+      // (addresses advance by pointer increments; no parameter re-reads, no per-group 64-bit index arithmetic): the general
+      // code spends ~140 instructions per 16-column group and ~45 per timestep on that, a quarter of the epilogue.
+      bool epilogue_done = false;
+      if constexpr (I8) {
+        if (lean) {
+          epilogue_done = true;
+          for (int cc = col_lo; cc < last_col; cc += 16) {
+            if (trace && threadIdx.x == 0 && trace_it == 1) trace[64 + 4 * ((cc - col_lo) >> 4)] = clock64();
+            float sc_[16], sh_[16], v[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {       // warp-uniform shared-memory reads (broadcast)
+              const float4 a = *reinterpret_cast<const float4*>(aS + j);
+              const float4 b = *reinterpret_cast<const float4*>(aH + j);
+              sc_[j] = a.x; sc_[j + 1] = a.y; sc_[j + 2] = a.z; sc_[j + 3] = a.w;
+              sh_[j] = b.x; sh_[j + 1] = b.y; sh_[j + 2] = b.z; sh_[j + 3] = b.w;
+            }
+            if (v_via_smem && !first_pass) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = sv[j * kEpiThreads];
+            } else if (load_v_global) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float4 a = *reinterpret_cast<const float4*>(v_grp + h * chunk_stride);
+                const float4 b = *reinterpret_cast<const float4*>(v_grp + h * chunk_stride + 4);
+                v[8 * h] = a.x; v[8 * h + 1] = a.y; v[8 * h + 2] = a.z; v[8 * h + 3] = a.w;
+                v[8 * h + 4] = b.x; v[8 * h + 5] = b.y; v[8 * h + 6] = b.z; v[8 * h + 7] = b.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+            uint4 sum_raw[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};   // fp16 counts of the earlier passes
+            if (load_sum) {
+              sum_raw[0] = *reinterpret_cast<const uint4*>(sum_grp);
+              sum_raw[1] = *reinterpret_cast<const uint4*>(sum_grp + chunk_stride);
+            }
+            uint32_t cnt8[4] = {0u, 0u, 0u, 0u};     // this pass's counts, one byte per column
+            if (trace && threadIdx.x == 0 && trace_it == 1) trace[64 + 4 * ((cc - col_lo) >> 4) + 1] = clock64();
+            if (trace && threadIdx.x == 0 && trace_it < 7 && cc == col_lo) trace[3 + trace_it * 8 + 6] = clock64();
+            uint8_t* o = o_grp;
+            uint32_t ta = t_grp;
+            for (int tl = 0; tl < T_acc; ++tl) {
+              uint32_t hi[16], lo[16];
+              tc_ld16(ta, hi);
+              tc_ld16(ta + n_tile, lo);
+              ta += 2 * n_tile;
+              tc_ld_wait_on(hi);
+              tc_ld_wait_on(lo);
+              uint32_t packed[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                // (float)(256 * hi + lo): one rounding of the exact integer sum; then BN affine, charge, fire, reset
+                const float x = fmaf(__int2float_rn((int)hi[j] * 256 + (int)lo[j]), sc_[j], sh_[j]);
+                const float h = fmaf(__fsub_rn(x, v[j]), inv_tau, v[j]);
+                const uint32_t pat = 1u << (8 * (j & 3));
+                asm("{\n\t"
+                    ".reg .pred q;\n\t"
+                    "setp.ge.f32 q, %2, %3;\n\t"
+                    "selp.f32 %0, 0f00000000, %2, q;\n\t"
+                    "@q or.b32 %1, %1, %4;\n\t"
+                    "}"
+                    : "=f"(v[j]), "+r"(packed[j >> 2])
+                    : "f"(h), "f"(vth), "r"(pat));
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) cnt8[k] += packed[k];     // four byte counters per word (at most T <= 16)
+              if (valid && want_spk) {
+                *reinterpret_cast<uint4*>(o) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                *reinterpret_cast<uint4*>(o + plane) = make_uint4(packed[0] << 7, packed[1] << 7, packed[2] << 7, packed[3] << 7);
+              }
+              o += 2 * plane;
+            }
+            if (trace && threadIdx.x == 0 && trace_it < 7 && cc == col_lo) trace[3 + trace_it * 8 + 7] = clock64();
+            if (trace && threadIdx.x == 0 && trace_it == 1) trace[64 + 4 * ((cc - col_lo) >> 4) + 2] = clock64();
+            if (want_sum && valid) {   // byte counters of this pass -> fp16, added to the earlier passes' counts (exact)
+              __half2* cnt2 = reinterpret_cast<__half2*>(sum_raw);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const uint32_t w = cnt8[k >> 1] >> (16 * (k & 1));
+                cnt2[k] = __hadd2(cnt2[k], __halves2half2(__ushort2half_rn((unsigned short)(w & 0xFFu)),
+                                                          __ushort2half_rn((unsigned short)((w >> 8) & 0xFFu))));
+              }
+              *reinterpret_cast<uint4*>(sum_grp) = sum_raw[0];
+              *reinterpret_cast<uint4*>(sum_grp + chunk_stride) = sum_raw[1];
+            }
+            if (v_via_smem && !last_pass) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) sv[j * kEpiThreads] = v[j];
+            } else if (store_v_global) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                *reinterpret_cast<float4*>(v_grp + h * chunk_stride) = make_float4(v[8 * h], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3]);
+                *reinterpret_cast<float4*>(v_grp + h * chunk_stride + 4) = make_float4(v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]);
+              }
+            }
+            if (trace && threadIdx.x == 0 && trace_it == 1) trace[64 + 4 * ((cc - col_lo) >> 4) + 3] = clock64();
+            o_grp += grp_bytes;
+            if (v_grp != nullptr) v_grp += 2 * chunk_stride;
+            if (want_sum) sum_grp += 2 * chunk_stride;
+            sv += 16 * kEpiThreads;
+            aS += 16; aH += 16;
+            t_grp += 16;
+          }
+        }
+      }
+      for (int cc = col_lo; cc < col_hi && !epilogue_done; cc += 16) {
         const int n = n0 + cc;  // first output channel of this 16-column group (warp-uniform)
         if (n >= p.Cout) continue;  // zero-padded tail of the last N tile
+        if (trace && threadIdx.x == 0 && trace_it == 1) trace[64 + 4 * ((cc - col_lo) >> 4)] = clock64();
         float sc_[16], sh_[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {       // warp-uniform shared-memory reads (broadcast)
@@ -825,8 +960,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
             }
           };
           if (trace && threadIdx.x == 0 && trace_it < 7 && cc == col_lo) trace[3 + trace_it * 8 + 6] = clock64();   // state loaded
+          if (trace && threadIdx.x == 0 && trace_it == 1) trace[64 + 4 * ((cc - col_lo) >> 4) + 1] = clock64();
           if (fast_lif) lif_all(std::true_type{}); else lif_all(std::false_type{});
           if (trace && threadIdx.x == 0 && trace_it < 7 && cc == col_lo) trace[3 + trace_it * 8 + 7] = clock64();   // LIF of group 0 done
+          if (trace && threadIdx.x == 0 && trace_it == 1) trace[64 + 4 * ((cc - col_lo) >> 4) + 2] = clock64();
           if (valid && n < p.Cout) {
             if (want_sum) {
               if constexpr (I8) {   // byte counters of this pass -> fp16, added to the earlier passes' counts (exact)
@@ -854,6 +991,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
               }
             }
           }
+          if (trace && threadIdx.x == 0 && trace_it == 1) trace[64 + 4 * ((cc - col_lo) >> 4) + 3] = clock64();
         } else {
           // SD_OUT_MEAN_T on a T-summed input: (conv(sum_t s_t) * scale + T * shift) / T, channels-last fp32
           uint32_t acc[16];

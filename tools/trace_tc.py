@@ -33,7 +33,7 @@ def main():
         dp.run_tokens(x_t, 7)
     torch.cuda.synchronize()
     lib = _lib.lib()
-    trace = torch.zeros(296 * 64, dtype=torch.int64, device=dev)
+    trace = torch.zeros(296 * 128, dtype=torch.int64, device=dev)
     layers = [("conv2", dp.l2, dp.x1, dp.x2, None, None), ("conv3", dp.l3, dp.x2, dp.x3, None, None),
               ("conv4", dp.l4, dp.x3, dp.x4, None, None), ("conv5", dp.l5, dp.x4, dp.x5, dp.x5s, None),
               ("conv6", dp.l6, dp.x5s, dp.logits, None, dp.x1s)]
@@ -44,7 +44,7 @@ def main():
         a.record(); l.run(xi, xo, x2=x2, out_sum=xs); c.record()
         torch.cuda.synchronize()
         _lib.check(lib.sd_debug_tc_trace(None))
-        tr = trace.cpu().numpy().reshape(296, 64)
+        tr = trace.cpu().numpy().reshape(296, 128)
         used = tr[:, 0] != 0
         g = int(used.sum())
         tr = tr[used]
@@ -77,6 +77,16 @@ def main():
                 msg += (f"; group 0: state loaded after {int(np.median(g[:, base + 6] - g[:, base + 4]))}, "
                         f"LIF over the pass's timesteps {int(np.median(g[:, base + 7] - g[:, base + 6]))}")
             print(msg)
+        # warp 0's 16-column groups of pass 1: start -> state loaded -> LIF done -> end (and the gap to the next group)
+        gp = tr[tr[:, 64] != 0][:, 64:64 + 16].reshape(-1, 4, 4)
+        if len(gp):
+            gp = gp[(gp[:, :, 3] != 0).all(axis=1)]
+        if len(gp):
+            med = lambda a: np.median(a, axis=0).astype(int).tolist()   # noqa: E731
+            print(f"   pass 1, warp 0, per 16-column group: load state {med(gp[:, :, 1] - gp[:, :, 0])}, LIF {med(gp[:, :, 2] - gp[:, :, 1])}, "
+                  f"store {med(gp[:, :, 3] - gp[:, :, 2])}, between groups {med(gp[:, 1:, 0] - gp[:, :-1, 3])}; "
+                  f"acc ready -> first group {int(np.median(gp[:, 0, 0] - tr[tr[:, 64] != 0][:len(gp), 3 + 8 + 4]))}, "
+                  f"last group -> release {int(np.median(tr[tr[:, 64] != 0][:len(gp), 3 + 8 + 5] - gp[:, 3, 3]))}")
         # tail: last epilogue release -> exit
         last = np.zeros(len(tr), dtype=np.int64)
         for it in range(7):
