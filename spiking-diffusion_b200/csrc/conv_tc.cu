@@ -446,9 +446,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
         mbar_wait(b_empty(st.stage), st.phase ^ 1);
         if (lane == 0) mbar_expect_tx(b_full(st.stage), c.b_stage_bytes);
         __syncwarp();
-        // One bulk copy per stage (kBPieces = 1).  Measured: the weight stream arrives at ~16 B/clk per SM, which is what
-        // the MMAs of a stage consume at 2 timesteps per pass; cutting a stage into 8 concurrent copies was slower
-        // (conv5 MMA phase 58.6 k -> 62 k cycles), and one timestep per pass (twice the weight traffic) is weight-bound.
+        // One bulk copy per stage (kBPieces = 1).  Measured (tools/probe_bulk.cu, profiles/r02_experiments.md): a
+        // cp.async.bulk costs the issuing thread ~600 cycles whatever its size (12 KB: ~20 B/clk, 48 KB: ~78 B/clk per SM),
+        // so this loop delivers one tap per ~600-730 cycles -- enough for the 768 cycles the 12 MMAs of a tap take at
+        // 2 timesteps per pass, not for one timestep per pass (384); cutting a stage into 8 concurrent copies is slower
+        // (conv5 MMA phase 58.6 k -> 62 k cycles).  It is an issue-rate limit, not a bandwidth limit.
         if (lane < kBPieces) {
           const uint32_t piece = c.b_stage_bytes / kBPieces;        // stage sizes are multiples of 1 KB
           bulk_g2s(b_base + st.stage * c.b_stage_bytes + lane * piece,
