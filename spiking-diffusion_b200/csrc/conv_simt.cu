@@ -290,7 +290,9 @@ __global__ void __launch_bounds__(256) conv_real_tiled_kernel(const SimtParams p
 // and the LIF runs on a constant current.  One thread = one output pixel x 8 output channels, so every timestep's
 // spikes leave as ONE 16-byte store into the STF plane, consecutive lanes -> consecutive rows (coalesced); the
 // 8-channel weight slice is a warp-uniform 2 x float4 load per (tap, ci) from the packed [tap][ci][co] array.
-template <int TMAX>
+// FAST (hard reset to 0, tau a power of two) and OUT8 (u8 STF8 output) are template parameters and the t loop is rolled:
+// the kernel runs once per diffusion step on a cold instruction cache, so its size is part of its latency.
+template <bool FAST, bool OUT8>
 __global__ void __launch_bounds__(256) conv_real_const_lif_kernel(const SimtParams p) {
   const sd_conv_desc& d = p.d;
   const int T = d.T, Cout = d.C_out, Cin = d.C_in;
@@ -308,8 +310,7 @@ __global__ void __launch_bounds__(256) conv_real_const_lif_kernel(const SimtPara
   const float* __restrict__ xin = (const float*)p.in;
   const int64_t plane = (int64_t)d.H_in * d.W_in;
   const float inv_tau = 1.0f / d.tau;
-  int tau_exp;
-  const bool fast = frexpf(d.tau, &tau_exp) == 0.5f && d.hard_reset && d.v_reset == 0.f;
+  constexpr bool fast = FAST;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int chunk = (int)(i / npix);
     int pix = (int)(i - (int64_t)chunk * npix);
@@ -351,16 +352,19 @@ __global__ void __launch_bounds__(256) conv_real_const_lif_kernel(const SimtPara
       cnt[j] = 0.f;
     }
     __half* outp = (__half*)p.out;
-    const bool out8 = d.out_kind == SD_OUT_LIF8;
-#pragma unroll
-    for (int t = 0; t < TMAX; ++t) {
-      if (t < T) {
+    constexpr bool out8 = OUT8;
+    // A rolled loop on purpose: the kernel runs once per diffusion step on a cold instruction cache, and fully unrolled
+    // the T = 16 body is ~40 KB of straight-line code whose fetch alone took ~35 us of the 46 us launch (time grew with
+    // TMAX, not with the work).  Nothing in the body is indexed by t at compile time.
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+      {
         uint32_t pk[4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float h;
           bool s;
-          if (fast) {
+          if constexpr (fast) {
             h = fmaf(__fsub_rn(x[j], v[j]), inv_tau, v[j]);
             s = h >= d.v_threshold;
             v[j] = s ? 0.f : h;
@@ -371,7 +375,7 @@ __global__ void __launch_bounds__(256) conv_real_const_lif_kernel(const SimtPara
             v[j] = d.hard_reset ? (s ? d.v_reset : h) : (s ? __fsub_rn(h, d.v_threshold) : h);
           }
           cnt[j] += s ? 1.f : 0.f;
-          if (out8) {       // STF8: one byte per spike, 8 channels = half of a 16-byte row
+          if constexpr (out8) {       // STF8: one byte per spike, 8 channels = half of a 16-byte row
             const uint32_t bit = (s ? 1u : 0u) << (8 * (j & 3));
             if (j & 3) pk[j >> 2] |= bit; else pk[j >> 2] = bit;
           } else {
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(256) conv_real_const_lif_kernel(const SimtPara
             if (j & 1) pk[j >> 1] |= bits << 16; else pk[j >> 1] = bits;
           }
         }
-        if (out8) {
+        if constexpr (out8) {
           const int64_t plane = (int64_t)(Cout8 >> 1) * gout.R_alloc * 16;
           uint8_t* o = (uint8_t*)p.out + (int64_t)(t * 2) * plane + ((int64_t)(chunk >> 1) * gout.R_alloc + orow) * 16 +
                        (chunk & 1) * 8;
@@ -790,10 +794,13 @@ int sd_conv_lif_simt(const sd_conv_desc* d, const sd_conv_args* a, void* stream)
     int64_t n8 = (int64_t)d->B * d->H_out * d->W_out * (d->C_out / 8);
     int64_t bl = (n8 + 255) / 256;
     if (bl > cap) bl = cap;
-    if (d->T <= 4) conv_real_const_lif_kernel<4><<<(unsigned)bl, 256, w_smem, st>>>(p);
-    else if (d->T <= 8) conv_real_const_lif_kernel<8><<<(unsigned)bl, 256, w_smem, st>>>(p);
-    else if (d->T <= 16) conv_real_const_lif_kernel<16><<<(unsigned)bl, 256, w_smem, st>>>(p);
-    else conv_real_const_lif_kernel<32><<<(unsigned)bl, 256, w_smem, st>>>(p);
+    int tau_exp;
+    const bool fast = frexpf(d->tau, &tau_exp) == 0.5f && d->hard_reset && d->v_reset == 0.f;
+    const bool out8 = d->out_kind == SD_OUT_LIF8;
+    if (fast && out8) conv_real_const_lif_kernel<true, true><<<(unsigned)bl, 256, w_smem, st>>>(p);
+    else if (fast) conv_real_const_lif_kernel<true, false><<<(unsigned)bl, 256, w_smem, st>>>(p);
+    else if (out8) conv_real_const_lif_kernel<false, true><<<(unsigned)bl, 256, w_smem, st>>>(p);
+    else conv_real_const_lif_kernel<false, false><<<(unsigned)bl, 256, w_smem, st>>>(p);
     SD_LAUNCH_CHECK();
     return SD_OK;
   }
