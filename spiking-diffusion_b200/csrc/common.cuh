@@ -1,5 +1,6 @@
 // Shared helpers for libsd_b200.so (sm_100a only).
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -78,5 +79,23 @@ struct StfGeom {
 struct MemoutCoef { float c[SD_MAX_T]; };  // 0.8^(T-1-t), passed by value (kernel parameter)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Programmatic dependent launch (the kernels of one diffusion step form a chain of short launches on one stream).
+// pdl_launch_dependents(): the next kernel of the stream may be scheduled now (its blocks run their prologue -- barrier
+// set-up, TMEM allocation, weights -- while this grid is still working).  pdl_wait(): blocks until every grid this launch
+// depends on has completed and its writes are visible; a kernel launched with the attribute must execute it in every
+// thread before that thread touches anything an earlier kernel wrote, and before it writes global memory.  Both are no-ops
+// in a launch without the attribute.  SD_PDL=0 disables the attribute (sd_pdl_mode()).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// 0: never, 1 (default): for plans of at most two concurrent chains (sd_conv_desc.concurrent <= 2), 2: always.  Measured
+// (profiles/r02_experiments.md): +3 % for the single chain of the as-shipped 16 / 32-image batch, +5.5 % for the two chains
+// of a 64-image shard, neutral for two large chains; with 3-5 chains the early blocks only take SMs from the other chains'
+// kernels (-3 % at 96 images ... -9 % at cfg2's 256).
+inline int sd_pdl_mode() {
+  static const int mode = [] { const char* e = getenv("SD_PDL"); return e ? atoi(e) : 1; }();
+  return mode;
+}
+inline bool sd_pdl_enabled(int concurrent) { return sd_pdl_mode() == 2 || (sd_pdl_mode() == 1 && concurrent <= 2); }
 
 }  // namespace sd

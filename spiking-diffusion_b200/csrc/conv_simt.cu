@@ -299,8 +299,10 @@ __global__ void __launch_bounds__(256) conv_real_const_lif_kernel(const SimtPara
   // the whole weight block [kh*kw][C_in][C_out] (a few KB for the real-input layers: K-dim 9 / 18 / 16) is staged in
   // shared memory once per block; threads of a warp share the output-channel chunk, so the reads are broadcasts
   extern __shared__ float sw[];
-  for (int i = threadIdx.x; i < d.kh * d.kw * Cin * Cout; i += blockDim.x) sw[i] = p.w[i];
+  pdl_launch_dependents();
+  for (int i = threadIdx.x; i < d.kh * d.kw * Cin * Cout; i += blockDim.x) sw[i] = p.w[i];   // weights: not produced by a kernel of the chain
   __syncthreads();
+  pdl_wait();                // the tokens / input of this step, and the buffers written below
   const bool tokens = d.in_kind == SD_IN_TOKENS;
   const int64_t* __restrict__ tok = (const int64_t*)p.in;
   const int Cout8 = Cout >> 3;
@@ -797,10 +799,22 @@ int sd_conv_lif_simt(const sd_conv_desc* d, const sd_conv_args* a, void* stream)
     int tau_exp;
     const bool fast = frexpf(d->tau, &tau_exp) == 0.5f && d->hard_reset && d->v_reset == 0.f;
     const bool out8 = d->out_kind == SD_OUT_LIF8;
-    if (fast && out8) conv_real_const_lif_kernel<true, true><<<(unsigned)bl, 256, w_smem, st>>>(p);
-    else if (fast) conv_real_const_lif_kernel<true, false><<<(unsigned)bl, 256, w_smem, st>>>(p);
-    else if (out8) conv_real_const_lif_kernel<false, true><<<(unsigned)bl, 256, w_smem, st>>>(p);
-    else conv_real_const_lif_kernel<false, false><<<(unsigned)bl, 256, w_smem, st>>>(p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)bl);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = w_smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = sd_pdl_enabled(d->concurrent) ? 1 : 0;
+    cudaError_t lrc;
+    if (fast && out8) lrc = cudaLaunchKernelEx(&cfg, conv_real_const_lif_kernel<true, true>, p);
+    else if (fast) lrc = cudaLaunchKernelEx(&cfg, conv_real_const_lif_kernel<true, false>, p);
+    else if (out8) lrc = cudaLaunchKernelEx(&cfg, conv_real_const_lif_kernel<false, true>, p);
+    else lrc = cudaLaunchKernelEx(&cfg, conv_real_const_lif_kernel<false, false>, p);
+    SD_CUDA(lrc);
     SD_LAUNCH_CHECK();
     return SD_OK;
   }

@@ -344,6 +344,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
   constexpr int dbg = 0;
 #endif
   if (trace && threadIdx.x == 0) trace[0] = clock64();
+  // programmatic dependent launch: let the next kernel of the chain start its prologue now; this kernel's own prologue,
+  // its weight stream and its first MMAs' B operands do not depend on the previous kernel -- only the A producer and the
+  // epilogue warps wait for it (pdl_wait below)
+  if (threadIdx.x == 0) pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < c.a_stages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); mbar_init(a_full_peer(s), 1); }
@@ -394,6 +398,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
 
   if (warp == kWarpA) {
     // ===== A producer =====
+    pdl_wait();                                      // the spikes are the previous kernel's output
     PipeState st;
     const int ncopy = c.T_acc * planes_t;
     for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
@@ -616,6 +621,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
     const float inv_tau = 1.0f / p.tau;
     const bool fast_lif = tau_pow2 && p.hard_reset && p.v_reset == 0.f;
     int trace_it = 0;
+    pdl_wait();                                      // before the first read of state / counts and the first store
     for (int tile = unit0, pass = 0; tile < total_tiles;
          (++pass == unit_passes) ? (pass = 0, tile += unit_stride) : 0) {
       const int tch = pass0_of(tile) + pass;
@@ -1045,6 +1051,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const TcParam
 template <bool FAST>
 __global__ void __launch_bounds__(256) lif_from_currents_kernel(const TcParams p) {
   constexpr int kChunk = 4;
+  pdl_launch_dependents();
+  pdl_wait();
   const float inv_tau = 1.0f / p.tau;
   int tau_exp;
   const bool tau_pow2 = frexpf(p.tau, &tau_exp) == 0.5f;
@@ -1709,13 +1717,15 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
     cfg.blockDim = dim3(kTcThreads);                                                                               \
     cfg.dynamicSmemBytes = c.smem_bytes;                                                                           \
     cfg.stream = st;                                                                                               \
-    cudaLaunchAttribute attr[1];                                                                                   \
+    cudaLaunchAttribute attr[2];                                                                                   \
     attr[0].id = cudaLaunchAttributeClusterDimension;                                                              \
     attr[0].val.clusterDim.x = PR ? 2 : 1;                                                                         \
     attr[0].val.clusterDim.y = 1;                                                                                  \
     attr[0].val.clusterDim.z = 1;                                                                                  \
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                               \
+    attr[1].val.programmaticStreamSerializationAllowed = 1;                                                        \
     cfg.attrs = attr;                                                                                              \
-    cfg.numAttrs = 1;                                                                                              \
+    cfg.numAttrs = sd_pdl_enabled(d->concurrent) ? 2 : 1;                                                          \
     SD_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<NS, KS, PR>, p));                                           \
   } while (0)
 #define SD_TC_LAUNCH(NS, KS)                                    \
@@ -1740,8 +1750,17 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
     if (bl > (int64_t)sm_count() * 8) bl = (int64_t)sm_count() * 8;
     int tau_exp;
     const bool fast = frexpf(p.tau, &tau_exp) == 0.5f && p.hard_reset && p.v_reset == 0.f;
-    if (fast) lif_from_currents_kernel<true><<<(unsigned)bl, 256, 0, st>>>(p);
-    else lif_from_currents_kernel<false><<<(unsigned)bl, 256, 0, st>>>(p);
+    cudaLaunchConfig_t lcfg = {};
+    lcfg.gridDim = dim3((unsigned)bl);
+    lcfg.blockDim = dim3(256);
+    lcfg.stream = st;
+    cudaLaunchAttribute lattr[1];
+    lattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    lattr[0].val.programmaticStreamSerializationAllowed = 1;
+    lcfg.attrs = lattr;
+    lcfg.numAttrs = sd_pdl_enabled(d->concurrent) ? 1 : 0;
+    if (fast) SD_CUDA(cudaLaunchKernelEx(&lcfg, lif_from_currents_kernel<true>, p));
+    else SD_CUDA(cudaLaunchKernelEx(&lcfg, lif_from_currents_kernel<false>, p));
     SD_LAUNCH_CHECK();
   }
   return SD_OK;

@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(256) sample_step_kernel(const float* __restric
                                                           int64_t n_tokens, int K, float inv_t, float inv_temp,
                                                           PhiloxCall cu, PhiloxCall ce, int64_t token_base,
                                                           const uint64_t* __restrict__ rng_dev) {
+  pdl_launch_dependents();   // the next step's conv1 may stage its weights while this grid samples
+  pdl_wait();
   if (rng_dev != nullptr) {
     // graph-replayable form: (seed, base offset) live in device memory; cu/ce carry offsets relative to the base
     const uint64_t seed = rng_dev[0], base4 = rng_dev[1] >> 2;
