@@ -161,3 +161,35 @@ def test_chunked_large_batch_equals_one_plan():
     ab.n_samples = 6
     lo = ab.sample(temp=1.0, sample_steps=49, seed=21, n_global=b, shard_base=0)
     assert torch.equal(lo, whole[:6])
+
+
+def test_programmatic_dependent_launch_does_not_change_the_samples():
+    """SD_PDL (csrc/common.cuh) lets the next kernel of the per-step chain start under the previous one's tail.  The knob is
+    read once per process, so two fresh interpreters sample the same 70 images (two concurrent chains, T = 4 and the
+    T-parallel T = 8 path) with it off and always on; tokens and decoded images must be identical."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, hashlib, torch\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
+        "from conftest import make_denoiser, make_vqvae\n"
+        "from spiking_diffusion_b200.snn_model.vq_diffusion import AbsorbingDiffusion\n"
+        "h = hashlib.sha256()\n"
+        "for T, b in ((4, 70), (8, 12)):\n"
+        "    den, _ = make_denoiser(T, 128, seed=3)\n"
+        "    vae, _ = make_vqvae(T, 128, seed=3)\n"
+        "    ab = AbsorbingDiffusion(den, mask_id=128, shape=(7, 7), n_samples=b)\n"
+        "    x = ab.sample(temp=0.9, sample_steps=49, seed=11)\n"
+        "    img = vae.decode_indices(x.reshape(b, 7, 7))\n"
+        "    h.update(x.cpu().numpy().tobytes()); h.update(img.cpu().numpy().tobytes())\n"
+        "print('DIGEST', h.hexdigest())\n")
+    digests = []
+    for mode in ("0", "2"):
+        env = dict(os.environ, SD_PDL=mode)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.append([l for l in r.stdout.splitlines() if l.startswith("DIGEST")][-1])
+    assert digests[0] == digests[1], digests
