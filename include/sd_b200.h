@@ -161,7 +161,10 @@ enum {
                              (decoder tail, R/snn_model/vae_model.py:152-153,186) */
   SD_OUT_MEAN_T = 3,    /* affine -> sum_t y_t / T -> fp32 [B, H_out, W_out, C_out] (channels last)
                              (denoiser read-out, R/snn_model/vq_diffusion.py:205-206) */
-  SD_OUT_LIF8 = 4       /* like SD_OUT_LIF with the spikes written as STF8 (u8); the optional T-sum stays fp16 STF */
+  SD_OUT_LIF8 = 4,      /* like SD_OUT_LIF with the spikes written as STF8 (u8); the optional T-sum stays fp16 STF */
+  SD_OUT_CURRENT_SEQ = 5 /* sd_conv_lif_tc with nsplit = 3 only: affine only (the un-fused layer.Conv2d of the training
+                           branch on tensor cores) -> fp32 in the planar STF row geometry [T][C_out/8][R_alloc][8]; guard
+                           and pad rows are not written */
 };
 
 typedef struct sd_conv_desc {

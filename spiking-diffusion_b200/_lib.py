@@ -111,7 +111,7 @@ class ConvArgs(ctypes.Structure):
 
 
 IN_REAL_CONST, IN_REAL_SEQ, IN_STF, IN_STF8, IN_TOKENS = 0, 1, 2, 3, 4
-OUT_LIF, OUT_REAL_SEQ, OUT_MEMOUT_TANH, OUT_MEAN_T, OUT_LIF8 = 0, 1, 2, 3, 4
+OUT_LIF, OUT_REAL_SEQ, OUT_MEMOUT_TANH, OUT_MEAN_T, OUT_LIF8, OUT_CURRENT_SEQ = 0, 1, 2, 3, 4, 5
 SD_ERR_INVALID, SD_ERR_CUDA, SD_ERR_NO_DEVICE, SD_ERR_UNSUPPORTED = 1, 2, 3, 4
 
 _lib: Optional[ctypes.CDLL] = None

@@ -43,12 +43,33 @@ class _ConvFn(torch.autograd.Function):
     (SJ/activation_based/layer.py:164-173, 316-325)."""
 
     @staticmethod
+    def _tc_forward(x5, mod):
+        """Forward on the tcgen05 kind::i8 kernel for a spike input (tagged by LIFNode's training branch) when the layer is
+        one the kernel takes (3x3, stride 1, pad 1, C_in % 32 == 0, C_out % 16 == 0, even T <= 16, grid width <= 62):
+        u8 spikes x three exact int8 weight digits (22-bit weights: relative error <= 2^-22 per weight, far inside the 1e-5
+        bar of tests/test_gpu_training.py), int32 accumulation.  Returns None when not applicable (SD_TRAIN_TC=0: never)."""
+        if mod.transposed or os.environ.get("SD_TRAIN_TC", "1") == "0":
+            return None
+        T, B, _, H, W = x5.shape
+        try:
+            plan = engine.FusedLayer(mod, None, None, T=T, B=B, H_in=H, W_in=W, in_kind=_lib.IN_STF,
+                                     out_kind=_lib.OUT_CURRENT_SEQ, impl="tc", nsplit=3)
+        except ValueError:
+            return None
+        cur = plan.run(engine.stf8_from_nchw(x5), plan.alloc_out())
+        return engine.currents_to_nchw(cur, T, B, plan.C_out, plan.H_out, plan.W_out)
+
+    @staticmethod
     def forward(ctx, x5, weight, bias, mod):
         T, B, _, H, W = x5.shape
+        spikes_in = bool(getattr(x5, "_sd_is_spikes", False))
+        x5 = x5.contiguous().float()
+        # the CUDA-core plan also provides the descriptor the backward pass works from
         plan = engine.FusedLayer(mod, None, None, T=T, B=B, H_in=H, W_in=W, in_kind=_lib.IN_REAL_SEQ,
                                  out_kind=_lib.OUT_REAL_SEQ, impl="simt")
-        x5 = x5.contiguous().float()
-        y = plan.run(x5, plan.alloc_out())
+        y = _ConvFn._tc_forward(x5, mod) if spikes_in else None
+        if y is None:
+            y = plan.run(x5, plan.alloc_out())
         ctx.save_for_backward(x5, weight)
         ctx.meta = (plan.desc, bool(mod.transposed), tuple(mod.kernel_size), tuple(mod.stride), tuple(mod.padding),
                     bias is not None)

@@ -127,6 +127,7 @@ class LIFNode(BaseNode):
             self.v = v
             if self.store_v_seq:
                 raise NotImplementedError("store_v_seq is not available on the autograd path")
+            spikes._sd_is_spikes = True      # lets the next layer.Conv2d take the tensor-core forward (layer._ConvFn)
             return spikes
         v = self.v.contiguous()
         spikes = torch.empty_like(x_seq)

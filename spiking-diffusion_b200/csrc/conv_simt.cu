@@ -712,7 +712,8 @@ int validate_conv_desc(const sd_conv_desc* d) {
   SD_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->stride >= 1 && d->pad >= 0, "conv: bad kernel/stride/padding");
   SD_REQUIRE(d->in_kind >= SD_IN_REAL_CONST && d->in_kind <= SD_IN_TOKENS, "conv: bad in_kind %d", d->in_kind);
   if (d->in_kind == SD_IN_TOKENS) SD_REQUIRE(d->C_in == 2 && !d->transposed, "conv: SD_IN_TOKENS is the denoiser's 2-channel input");
-  SD_REQUIRE(d->out_kind >= SD_OUT_LIF && d->out_kind <= SD_OUT_LIF8, "conv: bad out_kind %d", d->out_kind);
+  SD_REQUIRE(d->out_kind >= SD_OUT_LIF && d->out_kind <= SD_OUT_CURRENT_SEQ, "conv: bad out_kind %d", d->out_kind);
+  if (d->out_kind == SD_OUT_CURRENT_SEQ) SD_REQUIRE(d->in_kind == SD_IN_STF8 && d->C_out % 16 == 0, "conv: SD_OUT_CURRENT_SEQ is the tensor-core int8 path's output (STF8 input, C_out %% 16 == 0)");
   if (d->in_kind == SD_IN_STF8) SD_REQUIRE(d->in_T == d->T && d->C_in0 == d->C_in && d->C_in % 16 == 0,
                                            "conv: STF8 input needs in_T == T, one segment, C_in %% 16 == 0");
   if (d->out_kind == SD_OUT_LIF8) SD_REQUIRE(d->C_out % 16 == 0, "conv: STF8 output needs C_out %% 16 == 0");

@@ -1201,7 +1201,10 @@ static int tc_supported(const sd_conv_desc* d, const char** why) {
   const bool i8 = d->nsplit == 3;
   if (i8) {
     if (d->in_kind != SD_IN_STF8) { *why = "nsplit = 3 (int8 digits) takes STF8 (u8) spikes"; return 0; }
-    if (d->out_kind != SD_OUT_LIF8) { *why = "nsplit = 3 (int8 digits) writes STF8 spikes (out_kind LIF8)"; return 0; }
+    if (d->out_kind != SD_OUT_LIF8 && d->out_kind != SD_OUT_CURRENT_SEQ) {
+      *why = "nsplit = 3 (int8 digits) writes STF8 spikes (out_kind LIF8) or planar currents (CURRENT_SEQ)";
+      return 0;
+    }
     if (d->T % 2 || d->in_T != d->T || d->T > 16) { *why = "int8 path needs an even T <= 16 and in_T == T"; return 0; }
     if (d->C_in0 != d->C_in || d->C_in % 32 || d->C_out % 16) { *why = "int8 path needs C_in % 32 == 0, C_out % 16 == 0, one input segment"; return 0; }
     if (d->H_in != d->H_out || d->W_in != d->W_out) { *why = "output grid must equal input grid"; return 0; }
@@ -1245,6 +1248,9 @@ static int tc_config_i8(const sd_conv_desc* d, TcConfig* c) {
     const int64_t pair_units = (((int64_t)m_tiles + 1) / 2) * ((d->C_out + 127) / 128);
     if (pair_units * 4 <= sms) { c->tpar = 1; n_tile = 128; }
   }
+  // SD_OUT_CURRENT_SEQ (training branch: convolution only): every (tile, pass) is an independent unit whose epilogue
+  // writes x[t] = conv * scale + shift, exactly the first half of the T-parallel mode
+  if (d->out_kind == SD_OUT_CURRENT_SEQ) c->tpar = 1;
   if (knobs().ntile > 0) n_tile = knobs().ntile;
   while (n_tile > 32 && n_tile / 2 >= d->C_out) n_tile /= 2;
   if (!(n_tile == 32 || n_tile == 64 || n_tile == 128)) { set_error("conv_tc(i8): bad N tile %d", n_tile); return SD_ERR_UNSUPPORTED; }
@@ -1588,6 +1594,7 @@ int sd_conv_tc_supported(const sd_conv_desc* d) {
 int64_t sd_conv_workspace_bytes(const sd_conv_desc* d) {
   TcConfig c;
   if (!d || validate_conv_desc(d) != SD_OK || tc_config(d, &c) != SD_OK) return 0;
+  if (d->out_kind == SD_OUT_CURRENT_SEQ) return 0;                     // the currents go straight to args.out
   if (c.n_tchunks <= 1 || (!c.tpar && c.v_smem_off != 0)) return 0;   // potential carried in shared memory
   // one fp32 state plane [C_out/8][R_alloc][8]; in T-parallel mode one plane of currents per timestep instead
   const int64_t plane = (int64_t)c8(d->C_out) * stf_rows(d->B, d->H_out, d->W_out) * 8 * (int64_t)sizeof(float);
@@ -1661,7 +1668,11 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
   p.v = a->v ? a->v : (float*)a->workspace;
   p.v_load_initial = a->v != nullptr;
   p.v_store_final = a->v != nullptr;
-  if (c.tpar) {
+  const bool currents_only = d->out_kind == SD_OUT_CURRENT_SEQ;
+  if (currents_only) {
+    p.cur = (float*)a->out;
+    p.v = nullptr;
+  } else if (c.tpar) {
     SD_REQUIRE(a->workspace != nullptr, "conv_tc: this configuration needs args.workspace (sd_conv_workspace_bytes)");
     p.cur = (float*)a->workspace;
     p.v = a->v;
@@ -1673,13 +1684,13 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
   }
   if (d->out_kind == SD_OUT_LIF) { p.out_spk = (__half*)a->out; p.out_sum = (__half*)a->out_sum; }
   else if (d->out_kind == SD_OUT_LIF8) { p.out_spk8 = (uint8_t*)a->out; p.out_sum = (__half*)a->out_sum; }
-  else p.out_real = (float*)a->out;
+  else if (!currents_only) p.out_real = (float*)a->out;
   StfGeom g(d->B, d->H_in, d->W_in);
   p.R_alloc = g.R_alloc; p.G = g.G; p.R_valid = (int64_t)d->B * g.P;
   p.C8_0 = d->C_in0 / c.rowch; p.C8_1 = (d->C_in - d->C_in0) / c.rowch;   // 16-byte-row chunks per input segment
   p.Cout = d->C_out; p.Cout8 = c8(d->C_out);
   p.T = d->T; p.H = d->H_in; p.W = d->W_in; p.Wp = g.Wp; p.P = g.P;
-  p.nsplit = d->nsplit; p.out_kind = d->out_kind == SD_OUT_LIF8 ? SD_OUT_LIF : d->out_kind; p.hard_reset = d->hard_reset;
+  p.nsplit = d->nsplit; p.out_kind = (d->out_kind == SD_OUT_LIF8 || currents_only) ? SD_OUT_LIF : d->out_kind; p.hard_reset = d->hard_reset;
   p.tau = d->tau; p.v_th = d->v_threshold; p.v_reset = d->v_reset;
   // cute::UMMA::InstrDescriptor: c_format F32 (bit 4), a/b F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
   // kind::i8: c_format S32 (2 at bit 4), a_format u8 (0 at bit 7), b_format s8 (1 at bit 10)
@@ -1744,7 +1755,7 @@ int sd_conv_lif_tc(const sd_conv_desc* d, const sd_conv_args* a, void* stream) {
 #undef SD_TC_LAUNCH
 #undef SD_TC_LAUNCH_ONE
   SD_LAUNCH_CHECK();
-  if (c.tpar) {
+  if (c.tpar && !currents_only) {
     const int64_t n = (int64_t)p.Cout8 * p.R_valid;
     int64_t bl = (n + 255) / 256;
     if (bl > (int64_t)sm_count() * 8) bl = (int64_t)sm_count() * 8;

@@ -86,7 +86,7 @@ def stf_from_nchw(x: torch.Tensor) -> torch.Tensor:
 def stf8_from_nchw(x: torch.Tensor) -> torch.Tensor:
     """fp32 {0,1} spikes [T,B,C,H,W] -> STF8 (u8 planes of s and 128*s; the operand format of the kind::i8 layers)."""
     T, B, C, H, W = x.shape
-    out = torch.empty(lib().sd_stf_bytes(T, B, C, H, W), dtype=torch.uint8, device=x.device)
+    out = torch.zeros(lib().sd_stf_bytes(T, B, C, H, W), dtype=torch.uint8, device=x.device)   # guard / pad rows zero
     check(lib().sd_stf8_from_nchw(ptr(x.contiguous().float()), ptr(out), T, B, C, H, W, stream_ptr()))
     return out
 
@@ -167,10 +167,12 @@ class FusedLayer:
         d.nsplit = nsplit
         d.concurrent = int(concurrent)
         if nsplit == 3 and impl != "simt":
-            # kind::i8 layer: u8 spikes in and out (STF8)
-            if in_kind != _lib.IN_STF or out_kind != _lib.OUT_LIF:
-                raise ValueError("nsplit=3 (int8 weight digits) is a spike -> LIF layer")
-            d.in_kind, d.out_kind = _lib.IN_STF8, _lib.OUT_LIF8
+            # kind::i8 layer: u8 spikes in (STF8); u8 spikes out, or -- the training branch's un-fused convolution -- the
+            # fp32 currents in the planar row geometry (OUT_CURRENT_SEQ)
+            if in_kind != _lib.IN_STF or out_kind not in (_lib.OUT_LIF, _lib.OUT_CURRENT_SEQ):
+                raise ValueError("nsplit=3 (int8 weight digits) is a spike -> LIF (or spike -> current) layer")
+            d.in_kind = _lib.IN_STF8
+            d.out_kind = _lib.OUT_LIF8 if out_kind == _lib.OUT_LIF else _lib.OUT_CURRENT_SEQ
         if impl == "simt":
             d.nsplit = 2                      # unused by the CUDA-core kernels
         self.desc = d
@@ -246,6 +248,9 @@ class FusedLayer:
             return stf_empty(d.T, d.B, d.C_out, d.H_out, d.W_out, self.device)
         if d.out_kind == _lib.OUT_REAL_SEQ:
             return torch.empty((d.T, d.B, d.C_out, d.H_out, d.W_out), dtype=torch.float32, device=self.device)
+        if d.out_kind == _lib.OUT_CURRENT_SEQ:   # [T][C_out/8][R_alloc][8] fp32: twice the bytes of the fp16 STF tensor
+            return torch.empty(lib().sd_stf_bytes(d.T, d.B, d.C_out, d.H_out, d.W_out) // 2, dtype=torch.float32,
+                               device=self.device)
         if d.out_kind == _lib.OUT_MEMOUT_TANH:
             return torch.empty((d.B, d.C_out, d.H_out, d.W_out), dtype=torch.float32, device=self.device)
         return torch.empty((d.B, d.H_out, d.W_out, d.C_out), dtype=torch.float32, device=self.device)
@@ -362,6 +367,15 @@ class DenoiserPlan:
         self.xin[:, 0:1].copy_(x)
         self.xin[:, 1:2].copy_(t.to(self.xin.dtype).reshape(-1, 1, 1, 1).expand(-1, 1, self.h, self.w))
         return self.run_from_input()
+
+
+def currents_to_nchw(cur: torch.Tensor, T: int, B: int, C: int, H: int, W: int) -> torch.Tensor:
+    """OUT_CURRENT_SEQ buffer ([T][C/8][R_alloc][8] fp32, rows = guard + b*H*W + y*W + x) -> [T, B, C, H, W] fp32.
+    One strided copy; used by the training branch only (include/sd_b200.h: STF geometry)."""
+    guard = (W + 1 + 7) // 8 * 8
+    rows = cur.numel() // (T * (C // 8) * 8)
+    v = cur.view(T, C // 8, rows, 8)[:, :, guard:guard + B * H * W]
+    return v.reshape(T, C // 8, B, H, W, 8).permute(0, 2, 1, 5, 3, 4).reshape(T, B, C, H, W).contiguous()
 
 
 def cluster_count() -> int:

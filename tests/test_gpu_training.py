@@ -60,6 +60,41 @@ def test_conv_forward_and_gradients(cfg):
     assert rel_err(m.bias.grad, b_ref.grad) <= 1e-5
 
 
+@pytest.mark.parametrize("cfg", [dict(cin=64, cout=128, T=4, B=3, H=7), dict(cin=32, cout=16, T=2, B=5, H=8),
+                                 dict(cin=128, cout=48, T=8, B=2, H=5)])
+def test_spike_input_conv_forward_runs_on_tensor_cores(cfg, monkeypatch):
+    """Training branch: a 3x3 stride-1 layer.Conv2d fed by a LIFNode's spikes takes the tcgen05 kind::i8 kernel for its
+    forward (three exact int8 weight digits: 22-bit weights); output and all gradients against torch autograd, same bars
+    as the CUDA-core path.  SD_TRAIN_TC=0 switches it off."""
+    T, B, H, cin, cout = cfg["T"], cfg["B"], cfg["H"], cfg["cin"], cfg["cout"]
+    g = torch.Generator().manual_seed(3)
+    m = layer.Conv2d(cin, cout, 3, stride=1, padding=1, step_mode="m")
+    x = (torch.rand(T, B, cin, H, H, generator=g) < 0.2).float()
+    w_ref = m.weight.detach().clone().requires_grad_(True)
+    b_ref = m.bias.detach().clone().requires_grad_(True)
+    x_ref = x.clone().requires_grad_(True)
+    y_ref = F.conv2d(x_ref.flatten(0, 1), w_ref, b_ref, stride=1, padding=1)
+    gy = torch.randn(y_ref.shape, generator=g)
+    (y_ref * gy).sum().backward()
+    m = m.cuda().train()
+    xg = x.cuda().requires_grad_(True)
+    xg._sd_is_spikes = True                      # what LIFNode's training branch puts on its output
+    y_tc = layer._ConvFn._tc_forward(xg.detach(), m)
+    assert y_tc is not None and rel_err(y_tc, y_ref.view(y_tc.shape)) <= 1e-6      # the tensor-core result itself
+    y = m(xg)
+    assert torch.equal(y.detach(), y_tc)         # ... and the module took that path
+    (y * gy.view(y.shape).cuda()).sum().backward()
+    assert rel_err(xg.grad, x_ref.grad) <= 1e-5
+    assert rel_err(m.weight.grad, w_ref.grad) <= 1e-5
+    assert rel_err(m.bias.grad, b_ref.grad) <= 1e-5
+    monkeypatch.setenv("SD_TRAIN_TC", "0")
+    assert layer._ConvFn._tc_forward(xg.detach(), m) is None
+    # an untagged input or a shape the kernel does not take stays on the CUDA-core kernel
+    m2 = layer.Conv2d(24, 16, 3, stride=1, padding=1, step_mode="m").cuda().train()
+    monkeypatch.delenv("SD_TRAIN_TC")
+    assert layer._ConvFn._tc_forward(torch.zeros(T, B, 24, H, H, device="cuda"), m2) is None
+
+
 def test_batchnorm_train_mode_forward_backward_and_running_stats():
     C = 12
     g = torch.Generator().manual_seed(2)
