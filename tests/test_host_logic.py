@@ -286,3 +286,41 @@ def test_device_helpers_without_gpu():
     def f(x, k=1):
         return x + k
     assert float(f(torch.zeros(1), k=2)) == 2.0
+
+
+def test_current_seq_output_kind_descriptor_and_layout():
+    """SD_OUT_CURRENT_SEQ (the training branch's convolution on the int8 tensor-core path): accepted only with STF8 input and
+    nsplit = 3, needs no workspace, and engine.currents_to_nchw reads the planar [T][C/8][R_alloc][8] buffer back."""
+    import ctypes
+    import torch
+    from spiking_diffusion_b200 import _lib, engine
+    L = _lib.lib()
+
+    def desc(out_kind, nsplit=3, in_kind=None, C_in=64, C_out=48, T=4):
+        d = _lib.ConvDesc()
+        d.T, d.B, d.C_in, d.H_in, d.W_in, d.C_out, d.H_out, d.W_out = T, 3, C_in, 7, 7, C_out, 7, 7
+        d.kh = d.kw = 3
+        d.stride = d.pad = 1
+        d.in_kind = _lib.IN_STF8 if in_kind is None else in_kind
+        d.out_kind, d.in_T, d.C_in0 = out_kind, T, C_in
+        d.tau, d.v_threshold, d.v_reset, d.hard_reset, d.nsplit, d.concurrent = 2.0, 1.0, 0.0, 1, nsplit, 1
+        return d
+
+    ok = desc(_lib.OUT_CURRENT_SEQ)
+    assert L.sd_conv_tc_supported(ctypes.byref(ok)) == 1
+    assert L.sd_conv_workspace_bytes(ctypes.byref(ok)) == 0              # the currents go straight to args.out
+    assert L.sd_conv_weight_layout_tc(ctypes.byref(ok)) > 0
+    assert L.sd_conv_tc_supported(ctypes.byref(desc(_lib.OUT_CURRENT_SEQ, nsplit=2, in_kind=_lib.IN_STF))) == 0
+    assert L.sd_conv_tc_supported(ctypes.byref(desc(_lib.OUT_CURRENT_SEQ, T=3))) == 0      # int8 path: even T
+    assert L.sd_conv_tc_supported(ctypes.byref(desc(_lib.OUT_CURRENT_SEQ, C_in=24))) == 0  # C_in % 32
+    # layout: rows = guard + b*H*W + y*W + x, 8 channels innermost
+    T, B, C, H, W = 2, 3, 16, 5, 4
+    guard = (W + 1 + 7) // 8 * 8
+    rows = L.sd_stf_bytes(T, B, C, H, W) // 2 // (T * (C // 8) * 8)
+    want = torch.arange(T * B * C * H * W, dtype=torch.float32).reshape(T, B, C, H, W)
+    buf = torch.full((T, C // 8, rows, 8), float("nan"))
+    for t in range(T):
+        for c in range(C):
+            buf[t, c // 8, guard:guard + B * H * W, c % 8] = want[t, :, c].reshape(-1)
+    got = engine.currents_to_nchw(buf.reshape(-1), T, B, C, H, W)
+    assert torch.equal(got, want)
