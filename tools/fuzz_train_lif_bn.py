@@ -62,9 +62,10 @@ def main():
         errs = {"lif gx": e_lif, "lif v": e_v, "bn y": rel(yb.detach().cpu().flatten(0, 1), yr.detach()),
                 "bn gw": rel(bn.weight.grad.cpu(), ref.weight.grad), "bn gb": rel(bn.bias.grad.cpu(), ref.bias.grad),
                 "bn run_mean": rel(bn.running_mean.cpu(), ref.running_mean)}
-        if cnt > 1:   # with a single element per channel the variance and the input gradient are degenerate (0 / 0)
-            errs["bn gx"] = rel(xbg.grad.cpu().flatten(0, 1), xbr.grad)
+        if cnt > 1:   # with a single element per channel the variance is degenerate (0 / 0)
             errs["bn run_var"] = rel(bn.running_var.cpu(), ref.running_var)
+        if cnt > 2:   # with two elements the normalised values are +-1 and the input gradient cancels to O(eps): its
+            errs["bn gx"] = rel(xbg.grad.cpu().flatten(0, 1), xbr.grad)   # relative error measures fp32 cancellation only
         lim = {"bn gx": 2e-4}
         ok = same and all(v <= lim.get(k, 2e-5) for k, v in errs.items())
         bad += not ok
